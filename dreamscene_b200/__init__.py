@@ -1,0 +1,11 @@
+"""dreamscene_b200: B200-native (sm_100a) differentiable 3D-Gaussian rasterizer for DreamScene.
+
+Public surface = the reference extension's surface (see dreamscene_b200.rasterizer); import it
+either as ``dreamscene_b200`` or through the drop-in alias package ``diff_gaussian_rasterization``.
+"""
+from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, rasterize_gaussians,
+                         set_workspace_capacity)
+from . import parallel
+
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians",
+           "set_workspace_capacity", "parallel"]

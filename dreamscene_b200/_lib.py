@@ -1,0 +1,81 @@
+"""ctypes binding of libb200gsr.so (include/b200gsr.h).  Fails loudly if the library is missing:
+there is NO CPU or PyTorch fallback in the product path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb200gsr.so")
+
+EXPORTS = ["b200gsr_version", "b200gsr_last_error", "b200gsr_saved_layout_query",
+           "b200gsr_scratch_layout_query", "b200gsr_forward", "b200gsr_backward",
+           "b200gsr_mark_visible"]
+
+
+class Params(C.Structure):
+    _fields_ = [("P", C.c_int32), ("M", C.c_int32), ("sh_degree", C.c_int32),
+                ("image_height", C.c_int32), ("image_width", C.c_int32),
+                ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("scale_modifier", C.c_float),
+                ("prefiltered", C.c_int32), ("score_flag", C.c_int32),
+                ("bg", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p),
+                ("campos", C.c_void_p)]
+
+
+class SavedLayout(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in ("header", "tile_start", "work_order", "n_contrib",
+                                          "records", "total")]
+
+
+class ScratchLayout(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in ("counters", "tile_count", "tile_cursor", "rectdepth",
+                                          "geom", "keys", "dgeom", "total")]
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing. Build it with `python -m dreamscene_b200._build` "
+            "(needs nvcc; sm_100a only). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, sz, u64, u32, i32 = C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_int32
+    lib.b200gsr_version.restype = C.c_int
+    lib.b200gsr_last_error.restype = C.c_char_p
+    lib.b200gsr_saved_layout_query.argtypes = [i32, i32, i32, u64, C.POINTER(SavedLayout)]
+    lib.b200gsr_scratch_layout_query.argtypes = [i32, i32, i32, u64, C.POINTER(ScratchLayout)]
+    lib.b200gsr_forward.argtypes = [C.POINTER(Params)] + [vp] * 7 + [vp] * 4 + \
+        [vp, sz, vp, sz, u64, vp, u32, vp]
+    lib.b200gsr_backward.argtypes = [C.POINTER(Params)] + [vp] * 7 + [vp] * 4 + \
+        [vp, sz, vp, sz, u64] + [vp] * 8 + [vp]
+    lib.b200gsr_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]
+    for f in ("b200gsr_saved_layout_query", "b200gsr_scratch_layout_query", "b200gsr_forward",
+              "b200gsr_backward", "b200gsr_mark_visible"):
+        getattr(lib, f).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().b200gsr_last_error().decode("utf-8", "replace")
+
+
+def saved_layout(P: int, H: int, W: int, max_pairs: int) -> SavedLayout:
+    out = SavedLayout()
+    rc = load().b200gsr_saved_layout_query(P, H, W, max_pairs, C.byref(out))
+    if rc:
+        raise RuntimeError(f"b200gsr_saved_layout_query failed ({rc}): {last_error()}")
+    return out
+
+
+def scratch_layout(P: int, H: int, W: int, max_pairs: int) -> ScratchLayout:
+    out = ScratchLayout()
+    rc = load().b200gsr_scratch_layout_query(P, H, W, max_pairs, C.byref(out))
+    if rc:
+        raise RuntimeError(f"b200gsr_scratch_layout_query failed ({rc}): {last_error()}")
+    return out

@@ -1,0 +1,179 @@
+// C ABI (include/b200gsr.h): argument validation, buffer layouts, launch sequencing.
+#include "common.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return B200GSR_OK;
+    return fail(B200GSR_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+int validate_inputs(const b200gsr_params* p, const float* means3D, const float* shs,
+                    const float* colors, const float* opac, const float* scales,
+                    const float* rots, const float* cov3d) {
+    if (!p) return fail(B200GSR_ERR_BAD_ARG, "params is null");
+    if (p->P < 0 || p->image_height < 0 || p->image_width < 0)
+        return fail(B200GSR_ERR_BAD_ARG, "negative size");
+    if (p->image_height > 65535 * 16 || p->image_width > 65535 * 16)
+        return fail(B200GSR_ERR_UNSUPPORTED, "image larger than 65535 tiles per axis");
+    if (!p->bg || !p->viewmatrix || !p->projmatrix || !p->campos)
+        return fail(B200GSR_ERR_BAD_ARG, "bg/viewmatrix/projmatrix/campos must be device pointers");
+    if (p->P > 0) {
+        if (!means3D || !opac) return fail(B200GSR_ERR_BAD_ARG, "means3D/opacities are required");
+        if ((shs != nullptr) == (colors != nullptr))
+            return fail(B200GSR_ERR_BAD_ARG, "Please provide excatly one of either SHs or precomputed colors!");
+        const bool has_sr = scales != nullptr || rots != nullptr;
+        if (((scales == nullptr || rots == nullptr) && cov3d == nullptr) || (has_sr && cov3d != nullptr))
+            return fail(B200GSR_ERR_BAD_ARG,
+                        "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+        if (shs) {
+            if (p->sh_degree < 0 || p->sh_degree > 3)
+                return fail(B200GSR_ERR_UNSUPPORTED, "sh_degree %d not in 0..3", p->sh_degree);
+            if (p->M < (p->sh_degree + 1) * (p->sh_degree + 1) || p->M > 16)
+                return fail(B200GSR_ERR_BAD_ARG, "M=%d inconsistent with sh_degree=%d (need (deg+1)^2 <= M <= 16)",
+                            p->M, p->sh_degree);
+        }
+    }
+    return B200GSR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200gsr_version(void) { return B200GSR_VERSION; }
+
+const char* b200gsr_last_error(void) { return g_err; }
+
+int b200gsr_saved_layout_query(int32_t P, int32_t H, int32_t W, uint64_t max_pairs,
+                               b200gsr_saved_layout* out) {
+    if (!out || P < 0 || H < 0 || W < 0) return fail(B200GSR_ERR_BAD_ARG, "bad layout query");
+    if (max_pairs > 0xfffffff0ull) return fail(B200GSR_ERR_UNSUPPORTED, "max_pairs must fit in 32 bits");
+    const GsrTileGrid g = gsr_grid(H, W);
+    size_t off = 0;
+    out->header = off;      off = align_up(off + 8 * sizeof(uint32_t));
+    out->tile_start = off;  off = align_up(off + ((size_t)g.ntiles + 1) * sizeof(uint32_t));
+    out->work_order = off;  off = align_up(off + (size_t)g.ntiles * sizeof(uint32_t));
+    out->n_contrib = off;   off = align_up(off + (size_t)H * W * sizeof(uint32_t));
+    out->records = off;     off = align_up(off + (size_t)max_pairs * sizeof(GsrRec));
+    out->total = off;
+    return B200GSR_OK;
+}
+
+int b200gsr_scratch_layout_query(int32_t P, int32_t H, int32_t W, uint64_t max_pairs,
+                                 b200gsr_scratch_layout* out) {
+    if (!out || P < 0 || H < 0 || W < 0) return fail(B200GSR_ERR_BAD_ARG, "bad layout query");
+    if (max_pairs > 0xfffffff0ull) return fail(B200GSR_ERR_UNSUPPORTED, "max_pairs must fit in 32 bits");
+    const GsrTileGrid g = gsr_grid(H, W);
+    size_t off = 0;
+    out->counters = off;    off = align_up(off + 16 * sizeof(uint32_t));
+    out->tile_count = off;  off = align_up(off + (size_t)g.ntiles * sizeof(uint32_t));
+    out->tile_cursor = off; off = align_up(off + (size_t)g.ntiles * sizeof(uint32_t));
+    out->rectdepth = off;   off = align_up(off + (size_t)P * sizeof(uint4));
+    out->geom = off;        off = align_up(off + (size_t)P * sizeof(GsrRec));
+    out->keys = off;        off = align_up(off + (size_t)max_pairs * sizeof(uint64_t));
+    out->dgeom = off;       off = align_up(off + (size_t)P * 12 * sizeof(float));
+    out->total = off;
+    return B200GSR_OK;
+}
+
+int b200gsr_forward(const b200gsr_params* prm, const float* means3D, const float* shs,
+                    const float* colors_precomp, const float* opacities, const float* scales,
+                    const float* rotations, const float* cov3D_precomp, float* out_color,
+                    float* out_depth_alpha, int32_t* radii, float* score, void* scratch,
+                    size_t scratch_bytes, void* saved, size_t saved_bytes, uint64_t max_pairs,
+                    uint32_t* host_notify, uint32_t notify_seq, void* stream) {
+    int rc = validate_inputs(prm, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp);
+    if (rc) return rc;
+    if (!out_color || !out_depth_alpha || (prm->P > 0 && !radii) || !scratch || !saved)
+        return fail(B200GSR_ERR_BAD_ARG, "null output/workspace pointer");
+    if (prm->score_flag && prm->P > 0 && !score)
+        return fail(B200GSR_ERR_BAD_ARG, "score_flag set but score buffer is null");
+    GsrFwdArgs a;
+    a.prm = *prm;
+    if ((rc = b200gsr_scratch_layout_query(prm->P, prm->image_height, prm->image_width, max_pairs, &a.sl))) return rc;
+    if ((rc = b200gsr_saved_layout_query(prm->P, prm->image_height, prm->image_width, max_pairs, &a.vl))) return rc;
+    if (scratch_bytes < a.sl.total || saved_bytes < a.vl.total)
+        return fail(B200GSR_ERR_WORKSPACE, "workspace too small: scratch %zu < %zu or saved %zu < %zu",
+                    scratch_bytes, a.sl.total, saved_bytes, a.vl.total);
+    a.means3D = means3D; a.shs = shs; a.colors = colors_precomp; a.opac = opacities;
+    a.scales = scales; a.rots = rotations; a.cov3d = cov3D_precomp;
+    a.out_color = out_color; a.out_depth_alpha = out_depth_alpha; a.score = score; a.radii = radii;
+    a.scratch = static_cast<uint8_t*>(scratch); a.saved = static_cast<uint8_t*>(saved);
+    a.max_pairs = (uint32_t)max_pairs;
+    a.host_notify = host_notify; a.notify_seq = notify_seq;
+    a.stream = static_cast<cudaStream_t>(stream);
+
+    // counters + tile_count + tile_cursor are contiguous at the start of scratch: one memset
+    if ((rc = check_cuda(cudaMemsetAsync(a.scratch, 0, a.sl.rectdepth, a.stream), "memset"))) return rc;
+    if ((rc = check_cuda(gsr_launch_project(a), "project_sh"))) return rc;
+    if ((rc = check_cuda(gsr_launch_binning(a), "binning"))) return rc;
+    if ((rc = check_cuda(gsr_launch_composite_fwd(a), "composite_fwd"))) return rc;
+    return B200GSR_OK;
+}
+
+int b200gsr_backward(const b200gsr_params* prm, const float* means3D, const float* shs,
+                     const float* colors_precomp, const float* opacities, const float* scales,
+                     const float* rotations, const float* cov3D_precomp, const int32_t* radii,
+                     const float* out_depth_alpha, const float* dL_dcolor,
+                     const float* dL_ddepth_alpha, const void* saved, size_t saved_bytes,
+                     void* scratch, size_t scratch_bytes, uint64_t max_pairs, float* d_means3D,
+                     float* d_means2D, float* d_shs, float* d_colors, float* d_opacities,
+                     float* d_scales, float* d_rotations, float* d_cov3D, void* stream) {
+    int rc = validate_inputs(prm, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp);
+    if (rc) return rc;
+    if (prm->P == 0) return B200GSR_OK;
+    if (!radii || !out_depth_alpha || !dL_dcolor || !dL_ddepth_alpha || !saved || !scratch)
+        return fail(B200GSR_ERR_BAD_ARG, "null saved-state/gradient pointer");
+    if (!d_means3D || !d_means2D || !d_opacities || (shs && !d_shs) || (colors_precomp && !d_colors) ||
+        (cov3D_precomp && !d_cov3D) || (!cov3D_precomp && (!d_scales || !d_rotations)))
+        return fail(B200GSR_ERR_BAD_ARG, "null gradient output pointer");
+    GsrBwdArgs a;
+    a.prm = *prm;
+    if ((rc = b200gsr_scratch_layout_query(prm->P, prm->image_height, prm->image_width, max_pairs, &a.sl))) return rc;
+    if ((rc = b200gsr_saved_layout_query(prm->P, prm->image_height, prm->image_width, max_pairs, &a.vl))) return rc;
+    if (scratch_bytes < a.sl.total || saved_bytes < a.vl.total)
+        return fail(B200GSR_ERR_WORKSPACE, "workspace too small: scratch %zu < %zu or saved %zu < %zu",
+                    scratch_bytes, a.sl.total, saved_bytes, a.vl.total);
+    a.means3D = means3D; a.shs = shs; a.colors = colors_precomp; a.opac = opacities;
+    a.scales = scales; a.rots = rotations; a.cov3d = cov3D_precomp;
+    a.radii = radii; a.out_depth_alpha = out_depth_alpha;
+    a.dL_dcolor = dL_dcolor; a.dL_ddepth_alpha = dL_ddepth_alpha;
+    a.saved = static_cast<const uint8_t*>(saved); a.scratch = static_cast<uint8_t*>(scratch);
+    a.max_pairs = (uint32_t)max_pairs;
+    a.d_means3D = d_means3D; a.d_means2D = d_means2D; a.d_shs = d_shs; a.d_colors = d_colors;
+    a.d_opac = d_opacities; a.d_scales = d_scales; a.d_rots = d_rotations; a.d_cov3d = d_cov3D;
+    a.stream = static_cast<cudaStream_t>(stream);
+
+    if ((rc = check_cuda(cudaMemsetAsync(a.scratch + a.sl.counters, 0, 16 * sizeof(uint32_t), a.stream), "memset"))) return rc;
+    if ((rc = check_cuda(cudaMemsetAsync(a.scratch + a.sl.dgeom, 0, (size_t)prm->P * 12 * sizeof(float), a.stream), "memset"))) return rc;
+    if ((rc = check_cuda(gsr_launch_composite_bwd(a), "composite_bwd"))) return rc;
+    if ((rc = check_cuda(gsr_launch_project_bwd(a), "project_bwd"))) return rc;
+    return B200GSR_OK;
+}
+
+int b200gsr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
+                         const float* projmatrix, uint8_t* visible, void* stream) {
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !visible)))
+        return fail(B200GSR_ERR_BAD_ARG, "bad mark_visible arguments");
+    return check_cuda(gsr_launch_mark_visible(P, means3D, viewmatrix, projmatrix, visible,
+                                              static_cast<cudaStream_t>(stream)), "mark_visible");
+}
+
+}  // extern "C"

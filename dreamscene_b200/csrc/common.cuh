@@ -1,0 +1,160 @@
+// Shared device-side definitions for the B200 (sm_100a) Gaussian rasterizer kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200gsr.h"
+
+#define GSR_TILE 16
+#define GSR_NEAR_Z 0.2f
+#define GSR_ALPHA_MIN (1.0f / 255.0f)
+#define GSR_ALPHA_MAX 0.99f
+#define GSR_T_STOP 1e-4f
+#define GSR_LOG2E 1.4426950408889634f
+#define GSR_LN2 0.6931471805599453f
+
+// One (tile, Gaussian) pair as consumed by the composite kernels; also the per-Gaussian
+// "geom" record written by project_sh (the sort epilogue copies geom[idx] -> sorted[pos]).
+// 48 bytes = 3 x 16 B, so 8 consecutive lanes reading one 16-B part each hit 8 distinct
+// 4-bank groups (stride 12 words) -> conflict-free LDS.128, and tile lists are contiguous
+// 16-B-aligned byte ranges -> one cp.async.bulk (TMA) per chunk.
+struct __align__(16) GsrRec {
+    // part 0: everything the per-warp cull test needs
+    float px, py;   // pixel-space mean
+    uint32_t ext;   // half2 (ext_x, ext_y): conservative half extents of {alpha >= 1/255}
+    float A;        // scaled conic: log2(G) = A*dx*dx + B*dx*dy + C*dy*dy
+    // part 1
+    float B, C;     //   A = -0.5*log2e*conic.x, B = -log2e*conic.y, C = -0.5*log2e*conic.z
+    float opacity;
+    float depth;    // view-space z
+    // part 2
+    float r, g, b;  // colour (SH evaluated, +0.5, clamped >= 0) or colors_precomp
+    uint32_t idx;   // Gaussian index
+};
+static_assert(sizeof(GsrRec) == 48, "record must be 48 bytes");
+
+struct GsrTileGrid {
+    int gx, gy, ntiles;
+};
+
+__host__ __device__ inline GsrTileGrid gsr_grid(int H, int W) {
+    GsrTileGrid g;
+    g.gx = (W + GSR_TILE - 1) / GSR_TILE;
+    g.gy = (H + GSR_TILE - 1) / GSR_TILE;
+    g.ntiles = g.gx * g.gy;
+    return g;
+}
+
+// header words in the saved buffer
+enum { GSR_H_NUM_PAIRS = 0, GSR_H_MAX_PAIRS = 1, GSR_H_NUM_TILES = 2, GSR_H_OVERFLOW = 3,
+       GSR_H_NUM_BIG = 4, GSR_H_NUM_NONEMPTY = 5 };
+// counters in scratch
+enum { GSR_C_FWD_QUEUE = 0, GSR_C_BWD_QUEUE = 1, GSR_C_SORT_SMALL = 2, GSR_C_SORT_BIG = 3 };
+
+#define GSR_SORT_SMALL_MAX 4096   // keys sorted by the 256-thread kernel (32 KB smem)
+#define GSR_SORT_BIG_SMEM 16384   // keys per smem chunk of the 1024-thread kernel (128 KB)
+
+#ifdef __CUDACC__
+// ---- 128-bit global access helpers -------------------------------------------------------
+__device__ __forceinline__ float4 ldg_nc_f4(const void* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldg_f4(const void* p) {
+    return *reinterpret_cast<const float4*>(p);
+}
+__device__ __forceinline__ void stg_f4(void* p, float4 v) {
+    *reinterpret_cast<float4*>(p) = v;
+}
+__device__ __forceinline__ void stg_na_f4(void* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void red_add_f4(float* p, float4 v) {
+    // sm_90+: one 16-byte vector reduction instead of four scalar REDs
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ---- mbarrier + bulk async copy (TMA 1-D) -------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// global -> shared bulk copy, completion counted on an mbarrier (SASS: UBLKCP.S.G)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                         uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+#endif  // __CUDACC__
+
+// ---- kernel launchers (defined in the .cu files, called from api.cu) ---------------------
+struct GsrFwdArgs {
+    b200gsr_params prm;
+    const float *means3D, *shs, *colors, *opac, *scales, *rots, *cov3d;
+    float *out_color, *out_depth_alpha, *score;
+    int32_t* radii;
+    uint8_t *scratch, *saved;
+    b200gsr_scratch_layout sl;
+    b200gsr_saved_layout vl;
+    uint32_t max_pairs;
+    uint32_t* host_notify;
+    uint32_t notify_seq;
+    cudaStream_t stream;
+};
+
+struct GsrBwdArgs {
+    b200gsr_params prm;
+    const float *means3D, *shs, *colors, *opac, *scales, *rots, *cov3d;
+    const int32_t* radii;
+    const float *out_depth_alpha, *dL_dcolor, *dL_ddepth_alpha;
+    const uint8_t* saved;
+    uint8_t* scratch;
+    b200gsr_scratch_layout sl;
+    b200gsr_saved_layout vl;
+    uint32_t max_pairs;
+    float *d_means3D, *d_means2D, *d_shs, *d_colors, *d_opac, *d_scales, *d_rots, *d_cov3d;
+    cudaStream_t stream;
+};
+
+cudaError_t gsr_launch_project(const GsrFwdArgs& a);
+cudaError_t gsr_launch_binning(const GsrFwdArgs& a);       // scan + order + scatter + sort
+cudaError_t gsr_launch_composite_fwd(const GsrFwdArgs& a);
+cudaError_t gsr_launch_composite_bwd(const GsrBwdArgs& a);
+cudaError_t gsr_launch_project_bwd(const GsrBwdArgs& a);
+cudaError_t gsr_launch_mark_visible(int P, const float* means3D, const float* view,
+                                    const float* proj, uint8_t* visible, cudaStream_t s);

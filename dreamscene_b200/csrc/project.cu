@@ -1,0 +1,569 @@
+// project_sh (forward) and project_bwd (backward): the per-Gaussian streaming stages.
+//
+// Replaces upstream's preprocessCUDA / computeCov2DCUDA / preprocessCUDA-backward
+// (comp-diff-gaussian-rasterization, un-vendored; functional spec: SURVEY.md App. A.1-A.5, A.7,
+// restated in oracle/splat_ref.py::preprocess).  The SH basis follows
+// /root/reference/utils/sh_utils.py:25-102, the covariance /root/reference/gs_renderer.py:124-157.
+//
+// Numerics contract: everything that decides an integer (depth bits, radius, tile rect) uses
+// individually rounded fp32 ops (__fmul_rn/__fadd_rn/... are never FMA-contracted) in the order
+// written in the oracle, so those integers are bit-exact against it.
+#include "common.cuh"
+#include <cuda_fp16.h>
+
+#define MUL(a, b) __fmul_rn((a), (b))
+#define ADD(a, b) __fadd_rn((a), (b))
+#define SUB(a, b) __fsub_rn((a), (b))
+#define DIV(a, b) __fdiv_rn((a), (b))
+#define SQRT(a) __fsqrt_rn((a))
+
+namespace {
+
+#define SH_C0 0.28209479177387814f
+#define SH_C1 0.4886025119029199f
+#define SH_C2_0 1.0925484305920792f
+#define SH_C2_1 -1.0925484305920792f
+#define SH_C2_2 0.31539156525252005f
+#define SH_C2_3 -1.0925484305920792f
+#define SH_C2_4 0.5462742152960396f
+#define SH_C3_0 -0.5900435899266435f
+#define SH_C3_1 2.890611442640554f
+#define SH_C3_2 -0.4570457994644658f
+#define SH_C3_3 0.3731763325901154f
+#define SH_C3_4 -0.4570457994644658f
+#define SH_C3_5 1.445305721320277f
+#define SH_C3_6 -0.5900435899266435f
+
+struct Cam {
+    float V[16];
+    float F[16];
+    float cam[3];
+};
+
+__device__ __forceinline__ void load_cam(const b200gsr_params& p, Cam& c) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        c.V[i] = __ldg(p.viewmatrix + i);
+        c.F[i] = __ldg(p.projmatrix + i);
+    }
+    c.cam[0] = __ldg(p.campos + 0);
+    c.cam[1] = __ldg(p.campos + 1);
+    c.cam[2] = __ldg(p.campos + 2);
+}
+
+// Geometry shared by forward and backward (bit-exact part).
+struct Geo {
+    float tx, ty, tz;        // view-space mean
+    float hx, hy, hw, pw;    // clip-space, 1/(w+eps)
+    float px, py;            // pixel mean
+    float S[6];              // cov3D xx,xy,xz,yy,yz,zz
+    float R[9], s[3];        // rotation, modified scales (only if !precomp)
+    float cx, cy;            // clamped t.x, t.y
+    bool in_x, in_y;
+    float fx, fy;
+    float J00, J02, J11, J12;
+    float M0[3], M1[3], N0[3], N1[3];
+    float a, b, c, det, det_inv;
+};
+
+__device__ __forceinline__ void geo_view(const Cam& C, float x, float y, float z, Geo& g) {
+    g.tx = ADD(ADD(ADD(MUL(C.V[0], x), MUL(C.V[4], y)), MUL(C.V[8], z)), C.V[12]);
+    g.ty = ADD(ADD(ADD(MUL(C.V[1], x), MUL(C.V[5], y)), MUL(C.V[9], z)), C.V[13]);
+    g.tz = ADD(ADD(ADD(MUL(C.V[2], x), MUL(C.V[6], y)), MUL(C.V[10], z)), C.V[14]);
+}
+
+__device__ __forceinline__ void geo_rest(const Cam& C, const b200gsr_params& p, float x, float y,
+                                         float z, const float* __restrict__ scales,
+                                         const float* __restrict__ rots,
+                                         const float* __restrict__ cov3d, int i, Geo& g) {
+    g.hx = ADD(ADD(ADD(MUL(C.F[0], x), MUL(C.F[4], y)), MUL(C.F[8], z)), C.F[12]);
+    g.hy = ADD(ADD(ADD(MUL(C.F[1], x), MUL(C.F[5], y)), MUL(C.F[9], z)), C.F[13]);
+    g.hw = ADD(ADD(ADD(MUL(C.F[3], x), MUL(C.F[7], y)), MUL(C.F[11], z)), C.F[15]);
+    g.pw = DIV(1.0f, ADD(g.hw, 1e-7f));
+    const float ndcx = MUL(g.hx, g.pw), ndcy = MUL(g.hy, g.pw);
+    const float Wf = (float)p.image_width, Hf = (float)p.image_height;
+    g.px = MUL(SUB(MUL(ADD(ndcx, 1.0f), Wf), 1.0f), 0.5f);
+    g.py = MUL(SUB(MUL(ADD(ndcy, 1.0f), Hf), 1.0f), 0.5f);
+
+    if (cov3d != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) g.S[k] = __ldg(cov3d + 6 * (size_t)i + k);
+    } else {
+        const float mod = p.scale_modifier;
+        g.s[0] = MUL(mod, __ldg(scales + 3 * (size_t)i + 0));
+        g.s[1] = MUL(mod, __ldg(scales + 3 * (size_t)i + 1));
+        g.s[2] = MUL(mod, __ldg(scales + 3 * (size_t)i + 2));
+        const float4 q = __ldg(reinterpret_cast<const float4*>(rots) + i);
+        const float r = q.x, qx = q.y, qy = q.z, qz = q.w;
+        g.R[0] = SUB(1.0f, MUL(2.0f, ADD(MUL(qy, qy), MUL(qz, qz))));
+        g.R[1] = MUL(2.0f, SUB(MUL(qx, qy), MUL(r, qz)));
+        g.R[2] = MUL(2.0f, ADD(MUL(qx, qz), MUL(r, qy)));
+        g.R[3] = MUL(2.0f, ADD(MUL(qx, qy), MUL(r, qz)));
+        g.R[4] = SUB(1.0f, MUL(2.0f, ADD(MUL(qx, qx), MUL(qz, qz))));
+        g.R[5] = MUL(2.0f, SUB(MUL(qy, qz), MUL(r, qx)));
+        g.R[6] = MUL(2.0f, SUB(MUL(qx, qz), MUL(r, qy)));
+        g.R[7] = MUL(2.0f, ADD(MUL(qy, qz), MUL(r, qx)));
+        g.R[8] = SUB(1.0f, MUL(2.0f, ADD(MUL(qx, qx), MUL(qy, qy))));
+        float L[9];
+#pragma unroll
+        for (int r_ = 0; r_ < 3; ++r_)
+#pragma unroll
+            for (int c_ = 0; c_ < 3; ++c_) L[3 * r_ + c_] = MUL(g.R[3 * r_ + c_], g.s[c_]);
+#define LDOT(i_, j_) ADD(ADD(MUL(L[3 * i_], L[3 * j_]), MUL(L[3 * i_ + 1], L[3 * j_ + 1])), \
+                         MUL(L[3 * i_ + 2], L[3 * j_ + 2]))
+        g.S[0] = LDOT(0, 0); g.S[1] = LDOT(0, 1); g.S[2] = LDOT(0, 2);
+        g.S[3] = LDOT(1, 1); g.S[4] = LDOT(1, 2); g.S[5] = LDOT(2, 2);
+#undef LDOT
+    }
+
+    const float limx = MUL(1.3f, p.tanfovx), limy = MUL(1.3f, p.tanfovy);
+    g.fx = DIV(Wf, MUL(2.0f, p.tanfovx));
+    g.fy = DIV(Hf, MUL(2.0f, p.tanfovy));
+    const float txtz = DIV(g.tx, g.tz), tytz = DIV(g.ty, g.tz);
+    g.in_x = (txtz >= -limx) && (txtz <= limx);
+    g.in_y = (tytz >= -limy) && (tytz <= limy);
+    g.cx = MUL(fminf(limx, fmaxf(-limx, txtz)), g.tz);
+    g.cy = MUL(fminf(limy, fmaxf(-limy, tytz)), g.tz);
+    const float tz2 = MUL(g.tz, g.tz);
+    g.J00 = DIV(g.fx, g.tz);
+    g.J02 = -DIV(MUL(g.fx, g.cx), tz2);
+    g.J11 = DIV(g.fy, g.tz);
+    g.J12 = -DIV(MUL(g.fy, g.cy), tz2);
+    // Wr[i][k] = V[4k+i]
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        g.M0[k] = ADD(MUL(g.J00, C.V[4 * k + 0]), MUL(g.J02, C.V[4 * k + 2]));
+        g.M1[k] = ADD(MUL(g.J11, C.V[4 * k + 1]), MUL(g.J12, C.V[4 * k + 2]));
+    }
+    const float Sg[9] = {g.S[0], g.S[1], g.S[2], g.S[1], g.S[3], g.S[4], g.S[2], g.S[4], g.S[5]};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        g.N0[j] = ADD(ADD(MUL(g.M0[0], Sg[j]), MUL(g.M0[1], Sg[3 + j])), MUL(g.M0[2], Sg[6 + j]));
+        g.N1[j] = ADD(ADD(MUL(g.M1[0], Sg[j]), MUL(g.M1[1], Sg[3 + j])), MUL(g.M1[2], Sg[6 + j]));
+    }
+    g.a = ADD(ADD(ADD(MUL(g.N0[0], g.M0[0]), MUL(g.N0[1], g.M0[1])), MUL(g.N0[2], g.M0[2])), 0.3f);
+    g.b = ADD(ADD(MUL(g.N0[0], g.M1[0]), MUL(g.N0[1], g.M1[1])), MUL(g.N0[2], g.M1[2]));
+    g.c = ADD(ADD(ADD(MUL(g.N1[0], g.M1[0]), MUL(g.N1[1], g.M1[1])), MUL(g.N1[2], g.M1[2])), 0.3f);
+    g.det = SUB(MUL(g.a, g.c), MUL(g.b, g.b));
+    g.det_inv = DIV(1.0f, g.det);
+}
+
+__device__ __forceinline__ int tile_coord(float v, int gmax) {
+    float t = MUL(v, 0.0625f);
+    if (isnan(t)) t = 0.0f;
+    t = fminf(fmaxf(t, -1.0f), (float)gmax + 1.0f);
+    int q = __float2int_rz(t);
+    return min(gmax, max(0, q));
+}
+
+// ---- SH ----------------------------------------------------------------------------------
+__device__ __forceinline__ void load_sh(const float* __restrict__ base, int nfloats, bool vec_ok,
+                                        float (&sh)[48]) {
+    if (vec_ok) {
+#pragma unroll
+        for (int q = 0; q < 12; ++q) {
+            if (4 * q < nfloats) {
+                const float4 v = ldg_nc_f4(base + 4 * q);
+                sh[4 * q] = v.x; sh[4 * q + 1] = v.y; sh[4 * q + 2] = v.z; sh[4 * q + 3] = v.w;
+            } else {
+                sh[4 * q] = sh[4 * q + 1] = sh[4 * q + 2] = sh[4 * q + 3] = 0.0f;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 48; ++j) sh[j] = (j < nfloats) ? __ldg(base + j) : 0.0f;
+    }
+}
+
+// basis values for degree <= 3 at unit direction (x,y,z): utils/sh_utils.py:73-102
+__device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, float (&B)[16]) {
+    B[0] = SH_C0;
+#pragma unroll
+    for (int k = 1; k < 16; ++k) B[k] = 0.0f;
+    if (deg > 0) {
+        B[1] = -SH_C1 * y; B[2] = SH_C1 * z; B[3] = -SH_C1 * x;
+        if (deg > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            B[4] = SH_C2_0 * xy; B[5] = SH_C2_1 * yz; B[6] = SH_C2_2 * (2.0f * zz - xx - yy);
+            B[7] = SH_C2_3 * xz; B[8] = SH_C2_4 * (xx - yy);
+            if (deg > 2) {
+                B[9] = SH_C3_0 * y * (3.0f * xx - yy);
+                B[10] = SH_C3_1 * xy * z;
+                B[11] = SH_C3_2 * y * (4.0f * zz - xx - yy);
+                B[12] = SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+                B[13] = SH_C3_4 * x * (4.0f * zz - xx - yy);
+                B[14] = SH_C3_5 * z * (xx - yy);
+                B[15] = SH_C3_6 * x * (xx - 3.0f * yy);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void sh_color(const float (&B)[16], const float (&sh)[48], int ncoef,
+                                         float (&raw)[3]) {
+    raw[0] = raw[1] = raw[2] = 0.5f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        if (k < ncoef) {
+            raw[0] = fmaf(B[k], sh[3 * k + 0], raw[0]);
+            raw[1] = fmaf(B[k], sh[3 * k + 1], raw[1]);
+            raw[2] = fmaf(B[k], sh[3 * k + 2], raw[2]);
+        }
+    }
+}
+
+// =========================================================================================
+// Forward: one Gaussian per thread.
+// =========================================================================================
+__global__ void __launch_bounds__(256)
+project_sh_kernel(b200gsr_params p, const float* __restrict__ means3D,
+                  const float* __restrict__ shs, const float* __restrict__ colors,
+                  const float* __restrict__ opac, const float* __restrict__ scales,
+                  const float* __restrict__ rots, const float* __restrict__ cov3d,
+                  int32_t* __restrict__ radii, uint4* __restrict__ rectdepth,
+                  GsrRec* __restrict__ geom, uint32_t* __restrict__ tile_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.P) return;
+    Cam C;
+    load_cam(p, C);
+    const GsrTileGrid grid = gsr_grid(p.image_height, p.image_width);
+
+    const float x = __ldg(means3D + 3 * (size_t)i), y = __ldg(means3D + 3 * (size_t)i + 1),
+                z = __ldg(means3D + 3 * (size_t)i + 2);
+    Geo g;
+    geo_view(C, x, y, z, g);
+    int radius = 0;
+    uint4 rd = make_uint4(0u, 0u, __float_as_uint(g.tz), 0u);
+    if (g.tz > GSR_NEAR_Z) {
+        geo_rest(C, p, x, y, z, scales, rots, cov3d, i, g);
+        if (g.det != 0.0f) {
+            const float mid = MUL(0.5f, ADD(g.a, g.c));
+            const float sq = SQRT(fmaxf(SUB(MUL(mid, mid), g.det), 0.1f));
+            const float lam = fmaxf(ADD(mid, sq), SUB(mid, sq));
+            float rad_f = ceilf(MUL(3.0f, SQRT(lam)));
+            if (isnan(rad_f)) rad_f = 0.0f;
+            rad_f = fminf(fmaxf(rad_f, 0.0f), 1.0e9f);
+            const int minx = tile_coord(SUB(g.px, rad_f), grid.gx);
+            const int maxx = tile_coord(ADD(ADD(g.px, rad_f), 15.0f), grid.gx);
+            const int miny = tile_coord(SUB(g.py, rad_f), grid.gy);
+            const int maxy = tile_coord(ADD(ADD(g.py, rad_f), 15.0f), grid.gy);
+            const int touched = (maxx - minx) * (maxy - miny);
+            if (touched > 0) {
+                radius = (int)rad_f;
+                rd.x = (uint32_t)minx | ((uint32_t)miny << 16);
+                rd.y = (uint32_t)maxx | ((uint32_t)maxy << 16);
+                rd.w = (uint32_t)touched;
+
+                // colour
+                float rgb[3];
+                if (shs != nullptr) {
+                    float dx = x - C.cam[0], dy = y - C.cam[1], dz = z - C.cam[2];
+                    float dn = sqrtf(dx * dx + dy * dy + dz * dz);
+                    if (dn == 0.0f) dn = 1.0f;
+                    dx /= dn; dy /= dn; dz /= dn;
+                    const int ncoef = (p.sh_degree + 1) * (p.sh_degree + 1);
+                    float sh[48], B[16];
+                    load_sh(shs + (size_t)i * 3 * p.M, 3 * ncoef, (p.M & 3) == 0, sh);
+                    sh_basis(p.sh_degree, dx, dy, dz, B);
+                    sh_color(B, sh, ncoef, rgb);
+                    rgb[0] = fmaxf(rgb[0], 0.0f); rgb[1] = fmaxf(rgb[1], 0.0f); rgb[2] = fmaxf(rgb[2], 0.0f);
+                } else {
+                    rgb[0] = __ldg(colors + 3 * (size_t)i); rgb[1] = __ldg(colors + 3 * (size_t)i + 1);
+                    rgb[2] = __ldg(colors + 3 * (size_t)i + 2);
+                }
+                const float o = __ldg(opac + i);
+                // conservative half extents of the region where alpha can reach 1/255
+                float ex = -1.0f, ey = -1.0f;
+                if (o * 255.0f > 1.0f) {
+                    const float tau2 = 2.0f * __logf(o * 255.0f) * 1.01f + 0.01f;
+                    ex = sqrtf(tau2 * g.a) * 1.003f + 0.05f;
+                    ey = sqrtf(tau2 * g.c) * 1.003f + 0.05f;
+                    if (!(ex == ex)) ex = 65504.0f * 2.0f;   // NaN -> never cull
+                    if (!(ey == ey)) ey = 65504.0f * 2.0f;
+                }
+                const __half2 eh = __floats2half2_rn(ex, ey);
+                GsrRec rec;
+                rec.px = g.px; rec.py = g.py;
+                rec.A = -0.5f * GSR_LOG2E * MUL(g.c, g.det_inv);
+                rec.B = GSR_LOG2E * MUL(g.b, g.det_inv);          // -log2e * conic.y, conic.y = -b/det
+                rec.C = -0.5f * GSR_LOG2E * MUL(g.a, g.det_inv);
+                rec.opacity = o; rec.depth = g.tz; rec.idx = (uint32_t)i;
+                rec.r = rgb[0]; rec.g = rgb[1]; rec.b = rgb[2];
+                rec.ext = *reinterpret_cast<const uint32_t*>(&eh);
+                float4* dst = reinterpret_cast<float4*>(geom + i);
+                const float4* src = reinterpret_cast<const float4*>(&rec);
+                dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+
+                for (int ty = miny; ty < maxy; ++ty)
+                    for (int tx = minx; tx < maxx; ++tx) atomicAdd(tile_count + ty * grid.gx + tx, 1u);
+            }
+        }
+    }
+    radii[i] = radius;
+    rectdepth[i] = rd;
+}
+
+// =========================================================================================
+// Backward: one Gaussian per thread.  dgeom[i] = 12 accumulated floats from composite_bwd:
+//   0: sum g*(2A dx + B dy)   1: sum g*(2C dy + B dx)      (g = dL/dG * G, scaled conic)
+//   2: sum g*dx*dx  3: sum g*dx*dy  4: sum g*dy*dy
+//   5: sum G*dL/dalpha (dL/dopacity)   6..8: dL/drgb   9: dL/ddepth   10,11: unused
+// =========================================================================================
+__global__ void __launch_bounds__(256)
+project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
+                   const float* __restrict__ shs, const float* __restrict__ colors,
+                   const float* __restrict__ scales, const float* __restrict__ rots,
+                   const float* __restrict__ cov3d, const int32_t* __restrict__ radii,
+                   const float* __restrict__ dgeom,
+                   float* __restrict__ d_means3D, float* __restrict__ d_means2D,
+                   float* __restrict__ d_shs, float* __restrict__ d_colors,
+                   float* __restrict__ d_opac, float* __restrict__ d_scales,
+                   float* __restrict__ d_rots, float* __restrict__ d_cov3d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.P) return;
+    const bool vis = __ldg(radii + i) > 0;
+    const int nsh = 3 * p.M;
+    const bool vec_ok = (p.M & 3) == 0;
+    float dmean[3] = {0.f, 0.f, 0.f};
+    float dm2[2] = {0.f, 0.f};
+    float dop = 0.f;
+    float dsc[3] = {0.f, 0.f, 0.f};
+    float drot[4] = {0.f, 0.f, 0.f, 0.f};
+    float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float dcol[3] = {0.f, 0.f, 0.f};
+    float dsh[48];
+#pragma unroll
+    for (int j = 0; j < 48; ++j) dsh[j] = 0.f;
+
+    if (vis) {
+        Cam C;
+        load_cam(p, C);
+        const float x = __ldg(means3D + 3 * (size_t)i), y = __ldg(means3D + 3 * (size_t)i + 1),
+                    z = __ldg(means3D + 3 * (size_t)i + 2);
+        Geo g;
+        geo_view(C, x, y, z, g);
+        geo_rest(C, p, x, y, z, scales, rots, cov3d, i, g);
+        const float4 a0 = ldg_f4(dgeom + 12 * (size_t)i);
+        const float4 a1 = ldg_f4(dgeom + 12 * (size_t)i + 4);
+        const float4 a2 = ldg_f4(dgeom + 12 * (size_t)i + 8);
+        const float Wf = (float)p.image_width, Hf = (float)p.image_height;
+
+        // ---- mean2D -------------------------------------------------------------------------
+        const float dpx = GSR_LN2 * a0.x, dpy = GSR_LN2 * a0.y;   // dL/d(pixel mean)
+        const float dndcx = dpx * 0.5f * Wf, dndcy = dpy * 0.5f * Hf;
+        dm2[0] = dndcx; dm2[1] = dndcy;
+        const float pw = g.pw, pw2 = pw * pw;
+        const float mul1 = g.hx * pw2, mul2 = g.hy * pw2;
+        dmean[0] = (C.F[0] * pw - C.F[3] * mul1) * dndcx + (C.F[1] * pw - C.F[3] * mul2) * dndcy;
+        dmean[1] = (C.F[4] * pw - C.F[7] * mul1) * dndcx + (C.F[5] * pw - C.F[7] * mul2) * dndcy;
+        dmean[2] = (C.F[8] * pw - C.F[11] * mul1) * dndcx + (C.F[9] * pw - C.F[11] * mul2) * dndcy;
+
+        // ---- opacity, colour ----------------------------------------------------------------
+        dop = a1.y;
+        const float drgb[3] = {a1.z, a1.w, a2.x};
+        const float ddepth = a2.y;
+
+        // ---- conic -> cov2D -----------------------------------------------------------------
+        const float ga = -0.5f * a0.z, gb = -a0.w, gc = -0.5f * a1.x;   // dL/d(conic a,b,c)
+        const float ca = g.a, cb = g.b, cc = g.c;
+        const float di2 = g.det_inv * g.det_inv;
+        const float da = (-cc * cc * ga + cb * cc * gb - cb * cb * gc) * di2;
+        const float db = (2.f * cb * cc * ga - (ca * cc + cb * cb) * gb + 2.f * ca * cb * gc) * di2;
+        const float dc = (-cb * cb * ga + ca * cb * gb - ca * ca * gc) * di2;
+
+        // ---- cov2D -> cov3D (full, unsymmetrised) and -> M ----------------------------------
+        float Gs[9];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                Gs[3 * j + k] = da * g.M0[j] * g.M0[k] + db * g.M0[j] * g.M1[k] + dc * g.M1[j] * g.M1[k];
+        float dM0[3], dM1[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            dM0[j] = 2.f * da * g.N0[j] + db * g.N1[j];
+            dM1[j] = 2.f * dc * g.N1[j] + db * g.N0[j];
+        }
+        // M0k = J00*V[4k+0] + J02*V[4k+2] ; M1k = J11*V[4k+1] + J12*V[4k+2]
+        float dJ00 = 0.f, dJ02 = 0.f, dJ11 = 0.f, dJ12 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            dJ00 += dM0[k] * C.V[4 * k + 0];
+            dJ02 += dM0[k] * C.V[4 * k + 2];
+            dJ11 += dM1[k] * C.V[4 * k + 1];
+            dJ12 += dM1[k] * C.V[4 * k + 2];
+        }
+        const float tz = g.tz, itz = 1.0f / tz, itz2 = itz * itz, itz3 = itz2 * itz;
+        const float dcx = -g.fx * itz2 * dJ02;
+        const float dcy = -g.fy * itz2 * dJ12;
+        float dtz = -g.fx * itz2 * dJ00 - g.fy * itz2 * dJ11 + 2.f * g.fx * g.cx * itz3 * dJ02 +
+                    2.f * g.fy * g.cy * itz3 * dJ12;
+        const float dtx = g.in_x ? dcx : 0.f;
+        const float dty = g.in_y ? dcy : 0.f;
+        dtz += ddepth;
+        dmean[0] += C.V[0] * dtx + C.V[1] * dty + C.V[2] * dtz;
+        dmean[1] += C.V[4] * dtx + C.V[5] * dty + C.V[6] * dtz;
+        dmean[2] += C.V[8] * dtx + C.V[9] * dty + C.V[10] * dtz;
+
+        if (cov3d != nullptr) {
+            dcov[0] = Gs[0]; dcov[1] = Gs[1] + Gs[3]; dcov[2] = Gs[2] + Gs[6];
+            dcov[3] = Gs[4]; dcov[4] = Gs[5] + Gs[7]; dcov[5] = Gs[8];
+        } else {
+            // Sigma = L L^T, L = R diag(s): dL = (Gs + Gs^T) L
+            float L[9], dLm[9];
+#pragma unroll
+            for (int r_ = 0; r_ < 3; ++r_)
+#pragma unroll
+                for (int c_ = 0; c_ < 3; ++c_) L[3 * r_ + c_] = g.R[3 * r_ + c_] * g.s[c_];
+#pragma unroll
+            for (int r_ = 0; r_ < 3; ++r_)
+#pragma unroll
+                for (int c_ = 0; c_ < 3; ++c_) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) acc += (Gs[3 * r_ + k] + Gs[3 * k + r_]) * L[3 * k + c_];
+                    dLm[3 * r_ + c_] = acc;
+                }
+            float dR[9];
+#pragma unroll
+            for (int c_ = 0; c_ < 3; ++c_) {
+                dsc[c_] = p.scale_modifier *
+                          (dLm[c_] * g.R[c_] + dLm[3 + c_] * g.R[3 + c_] + dLm[6 + c_] * g.R[6 + c_]);
+#pragma unroll
+                for (int r_ = 0; r_ < 3; ++r_) dR[3 * r_ + c_] = dLm[3 * r_ + c_] * g.s[c_];
+            }
+            const float4 q = __ldg(reinterpret_cast<const float4*>(rots) + i);
+            const float r = q.x, qx = q.y, qy = q.z, qz = q.w;
+            drot[0] = 2.f * (-qz * dR[1] + qy * dR[2] + qz * dR[3] - qx * dR[5] - qy * dR[6] + qx * dR[7]);
+            drot[1] = 2.f * (qy * dR[1] + qz * dR[2] + qy * dR[3] - 2.f * qx * dR[4] - r * dR[5] +
+                             qz * dR[6] + r * dR[7] - 2.f * qx * dR[8]);
+            drot[2] = 2.f * (-2.f * qy * dR[0] + qx * dR[1] + r * dR[2] + qx * dR[3] + qz * dR[5] -
+                             r * dR[6] + qz * dR[7] - 2.f * qy * dR[8]);
+            drot[3] = 2.f * (-2.f * qz * dR[0] - r * dR[1] + qx * dR[2] + r * dR[3] - 2.f * qz * dR[4] +
+                             qy * dR[5] + qx * dR[6] + qy * dR[7]);
+        }
+
+        // ---- colour -> SH -------------------------------------------------------------------
+        if (shs != nullptr) {
+            float vx = x - C.cam[0], vy = y - C.cam[1], vz = z - C.cam[2];
+            float dn = sqrtf(vx * vx + vy * vy + vz * vz);
+            if (dn == 0.0f) dn = 1.0f;
+            const float inv_n = 1.0f / dn;
+            const float ux = vx / dn, uy = vy / dn, uz = vz / dn;
+            const int deg = p.sh_degree;
+            const int ncoef = (deg + 1) * (deg + 1);
+            float sh[48], B[16], raw[3];
+            load_sh(shs + (size_t)i * nsh, 3 * ncoef, vec_ok, sh);
+            sh_basis(deg, ux, uy, uz, B);
+            sh_color(B, sh, ncoef, raw);
+            float dc3[3];
+#pragma unroll
+            for (int c_ = 0; c_ < 3; ++c_) dc3[c_] = (raw[c_] < 0.0f) ? 0.0f : drgb[c_];
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                if (k < ncoef) {
+                    dsh[3 * k] = B[k] * dc3[0]; dsh[3 * k + 1] = B[k] * dc3[1]; dsh[3 * k + 2] = B[k] * dc3[2];
+                }
+            if (deg > 0) {
+                // s_k = sum_c dL/drgb_c * sh[k][c]
+                float s[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    s[k] = dc3[0] * sh[3 * k] + dc3[1] * sh[3 * k + 1] + dc3[2] * sh[3 * k + 2];
+                const float X = ux, Y = uy, Z = uz;
+                float gx = -SH_C1 * s[3], gy = -SH_C1 * s[1], gz = SH_C1 * s[2];
+                if (deg > 1) {
+                    gx += SH_C2_0 * Y * s[4] + SH_C2_2 * (-2.f * X) * s[6] + SH_C2_3 * Z * s[7] + SH_C2_4 * 2.f * X * s[8];
+                    gy += SH_C2_0 * X * s[4] + SH_C2_1 * Z * s[5] + SH_C2_2 * (-2.f * Y) * s[6] + SH_C2_4 * (-2.f * Y) * s[8];
+                    gz += SH_C2_1 * Y * s[5] + SH_C2_2 * 4.f * Z * s[6] + SH_C2_3 * X * s[7];
+                    if (deg > 2) {
+                        const float xx = X * X, yy = Y * Y, zz = Z * Z;
+                        gx += SH_C3_0 * 6.f * X * Y * s[9] + SH_C3_1 * Y * Z * s[10] + SH_C3_2 * (-2.f * X * Y) * s[11] +
+                              SH_C3_3 * (-6.f * X * Z) * s[12] + SH_C3_4 * (4.f * zz - 3.f * xx - yy) * s[13] +
+                              SH_C3_5 * 2.f * X * Z * s[14] + SH_C3_6 * (3.f * xx - 3.f * yy) * s[15];
+                        gy += SH_C3_0 * (3.f * xx - 3.f * yy) * s[9] + SH_C3_1 * X * Z * s[10] +
+                              SH_C3_2 * (4.f * zz - xx - 3.f * yy) * s[11] + SH_C3_3 * (-6.f * Y * Z) * s[12] +
+                              SH_C3_4 * (-2.f * X * Y) * s[13] + SH_C3_5 * (-2.f * Y * Z) * s[14] +
+                              SH_C3_6 * (-6.f * X * Y) * s[15];
+                        gz += SH_C3_1 * X * Y * s[10] + SH_C3_2 * 8.f * Y * Z * s[11] +
+                              SH_C3_3 * (6.f * zz - 3.f * xx - 3.f * yy) * s[12] + SH_C3_4 * 8.f * X * Z * s[13] +
+                              SH_C3_5 * (xx - yy) * s[14];
+                    }
+                }
+                // through d = v/|v|
+                const float dotg = X * gx + Y * gy + Z * gz;
+                dmean[0] += (gx - X * dotg) * inv_n;
+                dmean[1] += (gy - Y * dotg) * inv_n;
+                dmean[2] += (gz - Z * dotg) * inv_n;
+            }
+        } else {
+            dcol[0] = drgb[0]; dcol[1] = drgb[1]; dcol[2] = drgb[2];
+        }
+    }
+
+    // ---- dense writes (zeros for culled Gaussians) ---------------------------------------
+    d_means3D[3 * (size_t)i] = dmean[0]; d_means3D[3 * (size_t)i + 1] = dmean[1]; d_means3D[3 * (size_t)i + 2] = dmean[2];
+    d_means2D[3 * (size_t)i] = dm2[0]; d_means2D[3 * (size_t)i + 1] = dm2[1]; d_means2D[3 * (size_t)i + 2] = 0.f;
+    d_opac[i] = dop;
+    if (cov3d != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) d_cov3d[6 * (size_t)i + k] = dcov[k];
+    } else {
+        d_scales[3 * (size_t)i] = dsc[0]; d_scales[3 * (size_t)i + 1] = dsc[1]; d_scales[3 * (size_t)i + 2] = dsc[2];
+        reinterpret_cast<float4*>(d_rots)[i] = make_float4(drot[0], drot[1], drot[2], drot[3]);
+    }
+    if (shs != nullptr) {
+        float* dst = d_shs + (size_t)i * nsh;
+        if (vec_ok) {
+#pragma unroll
+            for (int q = 0; q < 12; ++q)
+                if (4 * q < nsh)
+                    stg_na_f4(dst + 4 * q, make_float4(dsh[4 * q], dsh[4 * q + 1], dsh[4 * q + 2], dsh[4 * q + 3]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 48; ++j)
+                if (j < nsh) dst[j] = dsh[j];
+        }
+    } else {
+        d_colors[3 * (size_t)i] = dcol[0]; d_colors[3 * (size_t)i + 1] = dcol[1]; d_colors[3 * (size_t)i + 2] = dcol[2];
+    }
+}
+
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
+                                    const float* __restrict__ V, uint8_t* __restrict__ visible) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float x = means3D[3 * (size_t)i], y = means3D[3 * (size_t)i + 1], z = means3D[3 * (size_t)i + 2];
+    const float tz = ADD(ADD(ADD(MUL(V[2], x), MUL(V[6], y)), MUL(V[10], z)), V[14]);
+    visible[i] = tz > GSR_NEAR_Z;
+}
+
+}  // namespace
+
+cudaError_t gsr_launch_project(const GsrFwdArgs& a) {
+    const int P = a.prm.P;
+    if (P == 0) return cudaSuccess;
+    project_sh_kernel<<<(P + 255) / 256, 256, 0, a.stream>>>(
+        a.prm, a.means3D, a.shs, a.colors, a.opac, a.scales, a.rots, a.cov3d, a.radii,
+        reinterpret_cast<uint4*>(a.scratch + a.sl.rectdepth),
+        reinterpret_cast<GsrRec*>(a.scratch + a.sl.geom),
+        reinterpret_cast<uint32_t*>(a.scratch + a.sl.tile_count));
+    return cudaGetLastError();
+}
+
+cudaError_t gsr_launch_project_bwd(const GsrBwdArgs& a) {
+    const int P = a.prm.P;
+    if (P == 0) return cudaSuccess;
+    project_bwd_kernel<<<(P + 255) / 256, 256, 0, a.stream>>>(
+        a.prm, a.means3D, a.shs, a.colors, a.scales, a.rots, a.cov3d, a.radii,
+        reinterpret_cast<const float*>(a.scratch + a.sl.dgeom), a.d_means3D, a.d_means2D, a.d_shs,
+        a.d_colors, a.d_opac, a.d_scales, a.d_rots, a.d_cov3d);
+    return cudaGetLastError();
+}
+
+cudaError_t gsr_launch_mark_visible(int P, const float* means3D, const float* view,
+                                    const float* /*proj*/, uint8_t* visible, cudaStream_t s) {
+    if (P == 0) return cudaSuccess;
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, view, visible);
+    return cudaGetLastError();
+}

@@ -1,0 +1,145 @@
+/*
+ * b200gsr.h - C ABI of the B200-native differentiable 3D-Gaussian rasterizer.
+ *
+ * This is the drop-in boundary for the ONE native op DreamScene calls on its render path:
+ * the un-vendored extension `diff_gaussian_rasterization._C`
+ * (DreamScene-Project/comp-diff-gaussian-rasterization; /root/reference/README.md:47,50,
+ * imported at /root/reference/scene_gaussian.py:11-12 and called at :637-646, :861-870,
+ * :1012-1021).  Upstream exposes it through pybind as
+ *     _C.rasterize_gaussians(...)            -> b200gsr_forward
+ *     _C.rasterize_gaussians_backward(...)   -> b200gsr_backward
+ *     _C.mark_visible(...)                   -> b200gsr_mark_visible (never called by DreamScene)
+ * Here the same three entry points are plain `extern "C"` functions over raw device pointers
+ * (no torch types), bound from Python with ctypes (dreamscene_b200/_lib.py) behind the
+ * byte-compatible GaussianRasterizationSettings / GaussianRasterizer Python surface.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless stated otherwise;
+ *     the library never allocates or frees device memory and keeps no global mutable state
+ *     (other than a thread-local error string);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no host sync;
+ *   - return value: 0 = OK, negative = error (see b200gsr_last_error());
+ *   - tensors are dense, row-major fp32 unless stated; layouts follow the reference call sites:
+ *       means3D[P,3] means2D-grad[P,3] shs[P,M,3] colors_precomp[P,3] opacities[P,1]
+ *       scales[P,3] rotations[P,4](w,x,y,z) cov3D_precomp[P,6](xx,xy,xz,yy,yz,zz)
+ *       out_color[3,H,W] out_depth_alpha[2,H,W] radii[P](int32) score[P]
+ *       viewmatrix/projmatrix[4,4] exactly as passed by scene_gaussian.py:586-599
+ *       (row-vector convention, flat index 4*row+col).
+ */
+#ifndef B200GSR_H
+#define B200GSR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200GSR_VERSION 1
+
+/* error codes */
+#define B200GSR_OK 0
+#define B200GSR_ERR_BAD_ARG (-1)      /* null pointer / inconsistent optional inputs */
+#define B200GSR_ERR_WORKSPACE (-2)    /* scratch/saved buffer too small for (P,H,W,max_pairs) */
+#define B200GSR_ERR_CUDA (-3)         /* a CUDA runtime call or launch failed */
+#define B200GSR_ERR_UNSUPPORTED (-4)  /* e.g. sh_degree > 3 */
+
+/* Per-call constants == GaussianRasterizationSettings (scene_gaussian.py:586-599) + sizes. */
+typedef struct b200gsr_params {
+    int32_t P;               /* number of Gaussians */
+    int32_t M;               /* SH coefficients per channel = (max_sh_degree+1)^2 (stride) */
+    int32_t sh_degree;       /* active degree, 0..3, (sh_degree+1)^2 <= M */
+    int32_t image_height;
+    int32_t image_width;
+    float tanfovx;
+    float tanfovy;
+    float scale_modifier;
+    int32_t prefiltered;     /* accepted for API compatibility; ignored (as upstream's render path) */
+    int32_t score_flag;      /* 1: also accumulate important_score[P] */
+    const float* bg;         /* device [3] */
+    const float* viewmatrix; /* device [16] */
+    const float* projmatrix; /* device [16] */
+    const float* campos;     /* device [3] */
+} b200gsr_params;
+
+/* Byte offsets of the arrays inside the `saved` buffer (for tests / debugging / backward). */
+typedef struct b200gsr_saved_layout {
+    size_t header;        /* uint32[8]: [0]=num_pairs (true D, may exceed max_pairs) [1]=max_pairs
+                             [2]=num_tiles [3]=overflow flag [4]=num_big_tiles [5..7] reserved */
+    size_t tile_start;    /* uint32[num_tiles+1] exclusive prefix of per-tile pair counts */
+    size_t work_order;    /* uint32[num_tiles] tile ids, longest list first */
+    size_t n_contrib;     /* uint32[H*W] index(1-based) of the last blended entry per pixel */
+    size_t records;       /* 48-byte records [max_pairs], tile-major, depth-sorted (see common.cuh) */
+    size_t total;
+} b200gsr_saved_layout;
+
+/* Byte offsets inside the transient `scratch` buffer (valid until the next call on the stream). */
+typedef struct b200gsr_scratch_layout {
+    size_t counters;      /* uint32[16] work-queue counters */
+    size_t tile_count;    /* uint32[num_tiles] */
+    size_t tile_cursor;   /* uint32[num_tiles] */
+    size_t rectdepth;     /* uint4[P]: (minx|miny<<16, maxx|maxy<<16, depth bits, tiles touched) */
+    size_t geom;          /* 48-byte records [P] in Gaussian order */
+    size_t keys;          /* uint64[max_pairs] (depth_bits<<32 | idx), tile-major, unsorted->sorted */
+    size_t dgeom;         /* backward only: float[P*12] screen-space gradient accumulators */
+    size_t total;
+} b200gsr_scratch_layout;
+
+int b200gsr_version(void);
+const char* b200gsr_last_error(void);
+
+/* Sizes/offsets of the two caller-owned buffers.  `saved` must stay alive until backward;
+ * `scratch` is transient.  max_pairs = capacity for (tile,Gaussian) pairs ("num_rendered"). */
+int b200gsr_saved_layout_query(int32_t P, int32_t H, int32_t W, uint64_t max_pairs,
+                               b200gsr_saved_layout* out);
+int b200gsr_scratch_layout_query(int32_t P, int32_t H, int32_t W, uint64_t max_pairs,
+                                 b200gsr_scratch_layout* out);
+
+/*
+ * Forward (replaces _C.rasterize_gaussians).  Exactly one of {shs, colors_precomp} and exactly
+ * one of {(scales, rotations), cov3D_precomp} must be non-null (same rule the reference Python
+ * enforces).  `score` may be null unless score_flag.  If the true pair count exceeds max_pairs the
+ * kernels stay in bounds, header[3] is set and the images are INVALID: the caller reads header[0]
+ * and re-issues the call with a larger capacity.  To learn the pair count without draining the
+ * stream, pass `host_notify` = a pinned, device-mapped HOST buffer of 4 uint32: as soon as the
+ * tile scan has run (long before compositing finishes) the device writes
+ * {notify_seq, num_pairs, overflow, num_tiles} into it (system-scope fence, seq written last);
+ * the host polls word 0.  Pass NULL to skip.
+ */
+int b200gsr_forward(const b200gsr_params* prm,
+                    const float* means3D, const float* shs, const float* colors_precomp,
+                    const float* opacities, const float* scales, const float* rotations,
+                    const float* cov3D_precomp,
+                    float* out_color, float* out_depth_alpha, int32_t* radii, float* score,
+                    void* scratch, size_t scratch_bytes, void* saved, size_t saved_bytes,
+                    uint64_t max_pairs, uint32_t* host_notify, uint32_t notify_seq, void* stream);
+
+/*
+ * Backward (replaces _C.rasterize_gaussians_backward).  Inputs as in forward plus the forward's
+ * radii / out_depth_alpha (channel 1 = final transmittance) / saved buffer and the incoming
+ * gradients dL/dcolor[3,H,W], dL/ddepth_alpha[2,H,W].  Outputs are fully overwritten (zeros for
+ * culled Gaussians): d_means3D[P,3], d_means2D[P,3] (NDC-scaled screen-space gradient, z=0),
+ * d_opacities[P,1], and d_shs[P,M,3] | d_colors[P,3], (d_scales[P,3], d_rotations[P,4]) |
+ * d_cov3D[P,6] matching the forward's input choice.
+ */
+int b200gsr_backward(const b200gsr_params* prm,
+                     const float* means3D, const float* shs, const float* colors_precomp,
+                     const float* opacities, const float* scales, const float* rotations,
+                     const float* cov3D_precomp,
+                     const int32_t* radii, const float* out_depth_alpha,
+                     const float* dL_dcolor, const float* dL_ddepth_alpha,
+                     const void* saved, size_t saved_bytes, void* scratch, size_t scratch_bytes,
+                     uint64_t max_pairs,
+                     float* d_means3D, float* d_means2D, float* d_shs, float* d_colors,
+                     float* d_opacities, float* d_scales, float* d_rotations, float* d_cov3D,
+                     void* stream);
+
+/* Frustum test only (replaces _C.mark_visible; DreamScene never calls it): visible[P] bytes. */
+int b200gsr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
+                         const float* projmatrix, uint8_t* visible, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GSR_H */
