@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py - forward+backward throughput of the rasterizer hot path (BASELINE.json metric:
+"fwd+bwd Mpix/s @1M Gaussians/1024^2; HBM GB/s vs roofline; 1/2/4/8 GPU").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one view of the workload rendered (forward) and back-propagated (backward) through
+the public drop-in API (GaussianRasterizer -> C ABI -> sm_100a kernels).  N>1 (torchrun, one
+rank per GPU): every rank renders its own view of the replicated scene (weak scaling: 1 view per
+GPU) and the parameter gradients are all-reduced over NCCL inside backward.
+
+Prints ONE JSON line (rank 0).  See the task contract for the keys; additions:
+  roofline      dominant kernel's algorithmic bytes / its measured launch time vs measured HBM peak
+  cpu_baseline  the pure-PyTorch CPU oracle timed on this box on a bounded sample (N=1 only)
+  stages_ms     mean device time of every kernel stage over the timed steps
+--impl reference times the CPU oracle port (the reference's CUDA op is un-vendored).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from dreamscene_b200 import cameras, synthetic  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: 1M Gaussians, 1024x1024 (object-like ball R=0.5) - the metric's config
+    "cfg3_1M_1024": dict(P=1_000_000, H=1024, W=1024, radius=0.5, opacity="sigmoid_normal"),
+    "cfg3b_1M_1024_screenfill": dict(P=1_000_000, H=1024, W=1024, radius=1.5, opacity="sigmoid_normal"),
+    "cfg2_100k_512": dict(P=100_000, H=512, W=512, radius=0.5, opacity="sigmoid_normal"),
+    "cfg1_10k_256": dict(P=10_000, H=256, W=256, radius=0.5, opacity="sigmoid_normal"),
+}
+METRIC = "fwd+bwd Mpix/s @1M Gaussians/1024^2"
+KERNELS_PER_STEP = 8   # project_sh, scan_order, scatter, sort_big, sort_small, composite_fwd, composite_bwd, project_bwd
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_scene(wl, view, device=None):
+    sc = synthetic.ball_scene(wl["P"], radius=wl["radius"], sh_degree_max=3, seed=0, opacity=wl["opacity"])
+    cam = cameras.orbit_camera(radius=3.5, theta_deg=60.0, phi_deg=45.0 * view, fovx=0.55,
+                               height=wl["H"], width=wl["W"])
+    g = torch.Generator().manual_seed(100 + view)
+    n = wl["H"] * wl["W"]
+    gc = torch.randn(3, wl["H"], wl["W"], generator=g) / n
+    gd = torch.randn(2, wl["H"], wl["W"], generator=g) / n
+    return sc, cam, gc, gd
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi in the background during the timed regions)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # median over the samples taken under load (power above the idle floor)
+        thr = min(power) + 0.3 * (max(power) - min(power))
+        load = [s for s, p in zip(sm, power) if p >= thr] or sm
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": float(max(power))}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (kind "port") on a bounded sample of the same workload
+# ---------------------------------------------------------------------------------------------
+def cpu_oracle_step(wl, view, sample_stride=64, threads=None):
+    """Full per-Gaussian stages on all P Gaussians + blending fwd/bwd on every `sample_stride`-th
+    tile (ordered by list length), scaled to the full frame by (tile,Gaussian)-pair count."""
+    from oracle import splat_ref as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    sc, cam, gc, gd = make_scene(wl, view)
+    S = O.Settings(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy, torch.ones(3), 1.0,
+                   cam.world_view_transform, cam.full_proj_transform, 3, cam.camera_center, False, False)
+    t = {k: v.clone().requires_grad_(True) for k, v in sc.items()}
+    m2d = torch.zeros(wl["P"], 3, requires_grad=True)
+    t0 = time.perf_counter()
+    pre = O.preprocess(S, t["means3D"], t["opacities"], shs=t["shs"], scales=t["scales"],
+                       rotations=t["rotations"], means2D=m2d)
+    t1 = time.perf_counter()
+    _, pl, ranges = O.bin_and_sort(pre, S)
+    t2 = time.perf_counter()
+    n = ranges[:, 1] - ranges[:, 0]
+    order = np.argsort(-n, kind="stable")
+    nonempty = int((n > 0).sum())
+    tiles = [int(x) for x in order[:max(nonempty, 1):sample_stride]]
+    pairs_total, pairs_sample = int(n.sum()), int(n[tiles].sum())
+    # leaves between the two stages so their backward passes can be timed separately
+    keys = ["px", "py", "opacity", "rgb", "depth"]
+    mid = {k: pre[k].detach().requires_grad_(True) for k in keys}
+    con = [c.detach().requires_grad_(True) for c in pre["conic"]]
+    pre2 = dict(pre); pre2.update(mid); pre2["conic"] = tuple(con)
+    t3 = time.perf_counter()
+    color, da, _, _ = O.composite(pre2, pl, ranges, S, tiles=tiles)
+    t4 = time.perf_counter()
+    loss = (color * gc).sum() + (da * gd).sum()
+    leaves = [mid[k] for k in keys] + con
+    g_mid = torch.autograd.grad(loss, leaves, allow_unused=True)
+    t5 = time.perf_counter()
+    outs = [pre[k] for k in keys] + list(pre["conic"])
+    pairs = [(o, g) for o, g in zip(outs, g_mid) if g is not None and o.requires_grad]
+    torch.autograd.backward([o for o, _ in pairs], [g for _, g in pairs])
+    t6 = time.perf_counter()
+    per_gauss = (t1 - t0) + (t2 - t1) + (t6 - t5)
+    blend = (t4 - t3) + (t5 - t4)
+    scale = pairs_total / max(pairs_sample, 1)
+    est_full = per_gauss + blend * scale
+    return dict(est_full_s=est_full, wall_s=t6 - t0, per_gaussian_s=per_gauss, blend_sample_s=blend,
+                pairs_total=pairs_total, pairs_sample=pairs_sample, tiles_sampled=len(tiles),
+                tiles_nonempty=nonempty, threads=threads)
+
+
+def cpu_baseline_dict(wl, r):
+    mpix = wl["H"] * wl["W"] / r["est_full_s"] / 1e6
+    return {"value": mpix, "unit": "Mpix/s", "cores": r["threads"], "kind": "port",
+            "sample": (f"oracle/splat_ref.py (pure PyTorch fp32, {r['threads']} threads): per-Gaussian stages "
+                       f"fwd+bwd on all {wl['P']} Gaussians ({r['per_gaussian_s']:.2f}s) + blending fwd+bwd on "
+                       f"{r['tiles_sampled']} of {r['tiles_nonempty']} non-empty tiles (every 64th by list length, "
+                       f"{r['pairs_sample']} of {r['pairs_total']} pairs, {r['blend_sample_s']:.2f}s) scaled by "
+                       f"pair count -> {r['est_full_s']:.1f}s per full step")}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(args, wl_name, wl, rank, world):
+    if rank != 0:
+        return
+    steps, warm = args.steps, args.warmup
+    res = []
+    for i in range(warm + steps):
+        r = cpu_oracle_step(wl, 0)
+        if i >= warm:
+            res.append(r)
+    est = float(np.mean([r["est_full_s"] for r in res]))
+    wall = float(np.mean([r["wall_s"] for r in res]))
+    r0 = dict(res[-1]); r0["est_full_s"] = est
+    cb = cpu_baseline_dict(wl, r0)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "Mpix/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": est * 1e3, "sampled_step_wall_ms": wall * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": wl_name, "P": wl["P"], "H": wl["H"], "W": wl["W"],
+                                            "note": "reference CUDA op is un-vendored; CPU oracle port timed"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def algorithmic_bytes(P, V, D, N, M):
+    """Minimum-traffic model per kernel (SURVEY.md 8d mapped onto this design)."""
+    g_in = 44 + 12 * M
+    return {
+        "project_sh": P * g_in + P * (4 + 16) + V * 48,        # params; radii + rect/depth; geom record
+        "scan_order": 0,
+        "scatter": P * 16 + D * 8,                               # rect/depth read; key write
+        "tile_sort": D * 8 + D * 48 + D * 48,                    # key read; record gather; record write
+        "composite_fwd": D * 48 + N * (12 + 8 + 4),              # records; colour, depth_alpha, n_contrib
+        "composite_bwd": D * 48 + N * (20 + 8) + V * 48,         # records; grads in + T/n_contrib; dgeom
+        "project_bwd": P * g_in + V * 48 + P * 4 + P * (g_in + 12),  # params, dgeom, radii; grads out
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3_1M_1024", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    wl_name, wl = args.workload, WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, wl_name, wl, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    from dreamscene_b200 import GaussianRasterizationSettings, GaussianRasterizer, _lib, parallel
+    from dreamscene_b200 import rasterizer as R
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback in the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        parallel.enable_view_sharding()
+    _lib.load()
+
+    sc, cam, gc_h, gd_h = make_scene(wl, rank)
+    P, H, W, M = wl["P"], wl["H"], wl["W"], 16
+    names = ("means3D", "opacities", "shs", "scales", "rotations")
+    host = {k: sc[k].pin_memory() for k in names}
+    prm = {k: host[k].to(dev).requires_grad_(True) for k in names}
+    gc, gd = gc_h.to(dev), gd_h.to(dev)
+    S = GaussianRasterizationSettings(
+        image_height=H, image_width=W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+        bg=torch.ones(3, device=dev), scale_modifier=1.0, viewmatrix=cam.world_view_transform.to(dev),
+        projmatrix=cam.full_proj_transform.to(dev), sh_degree=3, campos=cam.camera_center.to(dev),
+        prefiltered=False, score_flag=False)
+    rast = GaussianRasterizer(S)
+    m2d = torch.zeros(P, 3, device=dev, requires_grad=True)
+
+    def step(p):
+        for v in p.values():
+            v.grad = None
+        m2d.grad = None
+        color, radii, da = rast(means3D=p["means3D"], means2D=m2d, opacities=p["opacities"], shs=p["shs"],
+                                scales=p["scales"], rotations=p["rotations"])
+        torch.autograd.backward([color, da], [gc, gd])
+        return color, radii, da
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        _, radii, _ = step(prm)
+    barrier()
+    V = int((radii > 0).sum())
+    D = int(R._workspace(dev).last_pairs)
+
+    # ---- timed region 1: device-resident inputs --------------------------------------------
+    _lib.profile_enable(args.steps)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(prm)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    stages = _lib.profile_collect()
+    _lib.profile_enable(0)
+    t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_step = float(t_ms.item()) / args.steps
+    value = world * H * W / (ms_step * 1e-3) / 1e6
+
+    # ---- timed region 2: end to end with HOST buffers (H2D inputs, D2H results every step) --
+    e2e = None
+    if not args.no_e2e:
+        out_host = {"color": torch.empty(3, H, W).pin_memory(), "da": torch.empty(2, H, W).pin_memory(),
+                    "radii": torch.empty(P, dtype=torch.int32).pin_memory()}
+        grad_host = {k: torch.empty_like(host[k]).pin_memory() for k in names}
+        h2d = sum(host[k].numel() * 4 for k in names) + (16 + 16 + 3 + 3) * 4
+        d2h = sum(v.numel() * 4 for v in out_host.values()) + sum(v.numel() * 4 for v in grad_host.values())
+
+        def e2e_step():
+            p = {k: host[k].to(dev, non_blocking=True).requires_grad_(True) for k in names}
+            color, radii_, da = step(p)
+            out_host["color"].copy_(color.detach(), non_blocking=True)
+            out_host["da"].copy_(da.detach(), non_blocking=True)
+            out_host["radii"].copy_(radii_, non_blocking=True)
+            for k in names:
+                grad_host[k].copy_(p[k].grad, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()   # the caller owns host results after this
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(dt.item()) * 1e3 / args.steps
+        e2e = {"value": world * H * W / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+    clk = clocks.stop() if rank == 0 else None
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        alg = algorithmic_bytes(P, V, D, H * W, M)
+        mean_ms = {k: float(np.mean(v)) for k, v in stages.items() if v}
+        dom = max(mean_ms, key=mean_ms.get)
+        achieved = alg[dom] / (mean_ms[dom] * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(wl_name, {}).get(dom)
+            except Exception:
+                traffic = None
+        step_alg = sum(alg.values())
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl_name, "P": P, "H": H, "W": W, "sh_degree": 3, "M": M,
+                       "views_per_step": world, "parallelism": f"view-sharded dp{world}",
+                       "visible": V, "tile_pairs": D,
+                       "l2": "inputs larger than L2 (params 236 MB + records %d MB per step)" % (D * 48 // 2**20)},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": mean_ms[dom]},
+            "step_hbm": {"algorithmic_bytes": step_alg, "achieved_gbs": step_alg / (ms_step * 1e-3) / 1e9,
+                         "frac": step_alg / (ms_step * 1e-3) / 1e9 / peak},
+            "stages_ms": mean_ms,
+            "clocks": clk,
+            "gpu_launches": KERNELS_PER_STEP * args.steps,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_dict(wl, cpu_oracle_step(wl, 0))
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -10,7 +10,8 @@ LIB_PATH = os.path.join(HERE, "libb200gsr.so")
 
 EXPORTS = ["b200gsr_version", "b200gsr_last_error", "b200gsr_saved_layout_query",
            "b200gsr_scratch_layout_query", "b200gsr_forward", "b200gsr_backward",
-           "b200gsr_mark_visible"]
+           "b200gsr_mark_visible", "b200gsr_profile_enable", "b200gsr_profile_counts",
+           "b200gsr_profile_read"]
 
 
 class Params(C.Structure):
@@ -54,6 +55,11 @@ def load():
     lib.b200gsr_backward.argtypes = [C.POINTER(Params)] + [vp] * 7 + [vp] * 4 + \
         [vp, sz, vp, sz, u64] + [vp] * 8 + [vp]
     lib.b200gsr_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]
+    lib.b200gsr_profile_enable.argtypes = [i32]
+    lib.b200gsr_profile_counts.argtypes = [C.POINTER(i32), C.POINTER(i32)]
+    lib.b200gsr_profile_read.argtypes = [i32, i32, C.POINTER(C.c_float)]
+    for f in ("b200gsr_profile_enable", "b200gsr_profile_counts", "b200gsr_profile_read"):
+        getattr(lib, f).restype = C.c_int
     for f in ("b200gsr_saved_layout_query", "b200gsr_scratch_layout_query", "b200gsr_forward",
               "b200gsr_backward", "b200gsr_mark_visible"):
         getattr(lib, f).restype = C.c_int
@@ -78,4 +84,34 @@ def scratch_layout(P: int, H: int, W: int, max_pairs: int) -> ScratchLayout:
     rc = load().b200gsr_scratch_layout_query(P, H, W, max_pairs, C.byref(out))
     if rc:
         raise RuntimeError(f"b200gsr_scratch_layout_query failed ({rc}): {last_error()}")
+    return out
+
+
+FWD_STAGES = ("project_sh", "scan_order", "scatter", "tile_sort", "composite_fwd")
+BWD_STAGES = ("composite_bwd", "project_bwd")
+
+
+def profile_enable(max_calls: int) -> None:
+    rc = load().b200gsr_profile_enable(int(max_calls))
+    if rc:
+        raise RuntimeError(f"b200gsr_profile_enable failed ({rc}): {last_error()}")
+
+
+def profile_collect() -> dict:
+    """-> {stage: [ms per recorded call]} for every call recorded since profile_enable."""
+    lib = load()
+    nf, nb = C.c_int32(0), C.c_int32(0)
+    lib.b200gsr_profile_counts(C.byref(nf), C.byref(nb))
+    out = {k: [] for k in FWD_STAGES + BWD_STAGES}
+    buf = (C.c_float * 8)()
+    for i in range(nf.value):
+        if lib.b200gsr_profile_read(0, i, buf):
+            raise RuntimeError(last_error())
+        for k, name in enumerate(FWD_STAGES):
+            out[name].append(float(buf[k]))
+    for i in range(nb.value):
+        if lib.b200gsr_profile_read(1, i, buf):
+            raise RuntimeError(last_error())
+        for k, name in enumerate(BWD_STAGES):
+            out[name].append(float(buf[k]))
     return out

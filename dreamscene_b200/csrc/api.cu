@@ -24,6 +24,24 @@ int check_cuda(cudaError_t e, const char* what) {
     return fail(B200GSR_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
 }
 
+// ---- optional per-stage timing (process-wide, not thread-safe; used by bench.py only) ----------
+enum { kFwdEvents = 6, kBwdEvents = 3 };
+struct Prof {
+    int max_calls = 0;
+    int nfwd = 0, nbwd = 0;
+    cudaEvent_t* fwd = nullptr;   // [max_calls][kFwdEvents]
+    cudaEvent_t* bwd = nullptr;   // [max_calls][kBwdEvents]
+} g_prof;
+
+void prof_mark_fwd(int k, cudaStream_t s) {
+    if (g_prof.max_calls > 0 && g_prof.nfwd < g_prof.max_calls)
+        cudaEventRecord(g_prof.fwd[g_prof.nfwd * kFwdEvents + k], s);
+}
+void prof_mark_bwd(int k, cudaStream_t s) {
+    if (g_prof.max_calls > 0 && g_prof.nbwd < g_prof.max_calls)
+        cudaEventRecord(g_prof.bwd[g_prof.nbwd * kBwdEvents + k], s);
+}
+
 int validate_inputs(const b200gsr_params* p, const float* means3D, const float* shs,
                     const float* colors, const float* opac, const float* scales,
                     const float* rots, const float* cov3d) {
@@ -83,8 +101,8 @@ int b200gsr_scratch_layout_query(int32_t P, int32_t H, int32_t W, uint64_t max_p
     const GsrTileGrid g = gsr_grid(H, W);
     size_t off = 0;
     out->counters = off;    off = align_up(off + 16 * sizeof(uint32_t));
-    out->tile_count = off;  off = align_up(off + (size_t)g.ntiles * sizeof(uint32_t));
-    out->tile_cursor = off; off = align_up(off + (size_t)g.ntiles * sizeof(uint32_t));
+    out->tile_count = off;  off = align_up(off + (size_t)GSR_COPIES * g.ntiles * sizeof(uint32_t));
+    out->tile_cursor = off; off = align_up(off + (size_t)GSR_COPIES * g.ntiles * sizeof(uint32_t));
     out->rectdepth = off;   off = align_up(off + (size_t)P * sizeof(uint4));
     out->geom = off;        off = align_up(off + (size_t)P * sizeof(GsrRec));
     out->keys = off;        off = align_up(off + (size_t)max_pairs * sizeof(uint64_t));
@@ -120,11 +138,20 @@ int b200gsr_forward(const b200gsr_params* prm, const float* means3D, const float
     a.host_notify = host_notify; a.notify_seq = notify_seq;
     a.stream = static_cast<cudaStream_t>(stream);
 
-    // counters + tile_count + tile_cursor are contiguous at the start of scratch: one memset
-    if ((rc = check_cuda(cudaMemsetAsync(a.scratch, 0, a.sl.rectdepth, a.stream), "memset"))) return rc;
+    // counters + tile_count are contiguous at the start of scratch: one memset
+    if ((rc = check_cuda(cudaMemsetAsync(a.scratch, 0, a.sl.tile_cursor, a.stream), "memset"))) return rc;
+    prof_mark_fwd(0, a.stream);
     if ((rc = check_cuda(gsr_launch_project(a), "project_sh"))) return rc;
-    if ((rc = check_cuda(gsr_launch_binning(a), "binning"))) return rc;
+    prof_mark_fwd(1, a.stream);
+    if ((rc = check_cuda(gsr_launch_scan(a), "scan_order"))) return rc;
+    prof_mark_fwd(2, a.stream);
+    if ((rc = check_cuda(gsr_launch_scatter(a), "scatter"))) return rc;
+    prof_mark_fwd(3, a.stream);
+    if ((rc = check_cuda(gsr_launch_sort(a), "tile_sort"))) return rc;
+    prof_mark_fwd(4, a.stream);
     if ((rc = check_cuda(gsr_launch_composite_fwd(a), "composite_fwd"))) return rc;
+    prof_mark_fwd(5, a.stream);
+    if (g_prof.max_calls > 0 && g_prof.nfwd < g_prof.max_calls) ++g_prof.nfwd;
     return B200GSR_OK;
 }
 
@@ -163,8 +190,48 @@ int b200gsr_backward(const b200gsr_params* prm, const float* means3D, const floa
 
     if ((rc = check_cuda(cudaMemsetAsync(a.scratch + a.sl.counters, 0, 16 * sizeof(uint32_t), a.stream), "memset"))) return rc;
     if ((rc = check_cuda(cudaMemsetAsync(a.scratch + a.sl.dgeom, 0, (size_t)prm->P * 12 * sizeof(float), a.stream), "memset"))) return rc;
+    prof_mark_bwd(0, a.stream);
     if ((rc = check_cuda(gsr_launch_composite_bwd(a), "composite_bwd"))) return rc;
+    prof_mark_bwd(1, a.stream);
     if ((rc = check_cuda(gsr_launch_project_bwd(a), "project_bwd"))) return rc;
+    prof_mark_bwd(2, a.stream);
+    if (g_prof.max_calls > 0 && g_prof.nbwd < g_prof.max_calls) ++g_prof.nbwd;
+    return B200GSR_OK;
+}
+
+int b200gsr_profile_enable(int32_t max_calls) {
+    for (int i = 0; i < g_prof.max_calls * kFwdEvents; ++i) cudaEventDestroy(g_prof.fwd[i]);
+    for (int i = 0; i < g_prof.max_calls * kBwdEvents; ++i) cudaEventDestroy(g_prof.bwd[i]);
+    delete[] g_prof.fwd; delete[] g_prof.bwd;
+    g_prof = Prof();
+    if (max_calls <= 0) return B200GSR_OK;
+    g_prof.fwd = new cudaEvent_t[(size_t)max_calls * kFwdEvents];
+    g_prof.bwd = new cudaEvent_t[(size_t)max_calls * kBwdEvents];
+    for (int i = 0; i < max_calls * kFwdEvents; ++i)
+        if (cudaEventCreate(&g_prof.fwd[i]) != cudaSuccess) return fail(B200GSR_ERR_CUDA, "cudaEventCreate");
+    for (int i = 0; i < max_calls * kBwdEvents; ++i)
+        if (cudaEventCreate(&g_prof.bwd[i]) != cudaSuccess) return fail(B200GSR_ERR_CUDA, "cudaEventCreate");
+    g_prof.max_calls = max_calls;
+    return B200GSR_OK;
+}
+
+int b200gsr_profile_counts(int32_t* n_forward, int32_t* n_backward) {
+    if (n_forward) *n_forward = g_prof.nfwd;
+    if (n_backward) *n_backward = g_prof.nbwd;
+    return B200GSR_OK;
+}
+
+int b200gsr_profile_read(int32_t is_backward, int32_t call, float* ms) {
+    if (!ms) return fail(B200GSR_ERR_BAD_ARG, "ms is null");
+    const int n = is_backward ? g_prof.nbwd : g_prof.nfwd;
+    if (call < 0 || call >= n) return fail(B200GSR_ERR_BAD_ARG, "profile call index %d out of range (%d)", call, n);
+    const int ne = is_backward ? kBwdEvents : kFwdEvents;
+    cudaEvent_t* ev = (is_backward ? g_prof.bwd : g_prof.fwd) + (size_t)call * ne;
+    cudaError_t e = cudaEventSynchronize(ev[ne - 1]);
+    if (e != cudaSuccess) return check_cuda(e, "cudaEventSynchronize");
+    for (int k = 0; k + 1 < ne; ++k)
+        if ((e = cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1])) != cudaSuccess)
+            return check_cuda(e, "cudaEventElapsedTime");
     return B200GSR_OK;
 }
 

@@ -3,14 +3,17 @@
 // Replaces upstream's InclusiveSum + duplicateWithKeys + global 64-bit cub::DeviceRadixSort +
 // identifyTileRanges with a counting-sort by tile followed by
 // an independent in-shared-memory sort of every tile's list:
-//   project_sh        : per-tile pair counts (atomics)                       [project.cu]
-//   scan_order_kernel : exclusive scan -> tile_start[], cursors, total pair count, and the
-//                       work order (tiles bucketed by list length, longest first)
+//   project_sh        : per-tile pair counts (privatised RED atomics)             [project.cu]
+//   scan_order_kernel : exclusive scan -> tile_start[], per-copy cursors, total pair count, and
+//                       the work order (tiles bucketed by list length, longest first)
 //   scatter_kernel    : every Gaussian appends (depth_bits<<32 | idx) to each tile it touches
 //                       (arrival order inside a tile is arbitrary ...)
 //   sort kernels      : ... and is then fixed by sorting each tile's keys on (depth bits, idx):
 //                       identical to a stable sort of (tile<<32 | depth bits) over pairs emitted
 //                       in Gaussian-index order, i.e. bit-exact with the oracle's lists.
+//                       In-smem LSD radix sort (8-bit digits, ballot ranking, constant digit
+//                       bytes skipped) on the depth bits + a tie pass ordering equal depths by
+//                       index; lists longer than one chunk are merged with bitonic merge steps.
 //                       Epilogue gathers the 48-B record of every entry into the tile-major,
 //                       depth-sorted record array the composite kernels stream with TMA.
 #include "common.cuh"
@@ -39,7 +42,13 @@ scan_order_kernel(int ntiles, uint32_t max_pairs, const uint32_t* __restrict__ t
     __syncthreads();
     for (int base = 0; base < ntiles; base += 1024) {
         const int t = base + tid;
-        const uint32_t v = (t < ntiles) ? tile_count[t] : 0u;
+        uint32_t cnt[GSR_COPIES];
+        uint32_t v = 0;
+#pragma unroll
+        for (int c = 0; c < GSR_COPIES; ++c) {
+            cnt[c] = (t < ntiles) ? tile_count[(size_t)c * ntiles + t] : 0u;
+            v += cnt[c];
+        }
         uint32_t incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -61,7 +70,12 @@ scan_order_kernel(int ntiles, uint32_t max_pairs, const uint32_t* __restrict__ t
         const uint32_t excl = carry_s + warp_sums[wid] + incl - v;
         if (t < ntiles) {
             tile_start[t] = excl;
-            tile_cursor[t] = excl;
+            uint32_t run = excl;
+#pragma unroll
+            for (int c = 0; c < GSR_COPIES; ++c) {
+                tile_cursor[(size_t)c * ntiles + t] = run;
+                run += cnt[c];
+            }
             atomicAdd(&bucket_cnt[size_bucket(v)], 1u);
         }
         __syncthreads();
@@ -94,7 +108,10 @@ scan_order_kernel(int ntiles, uint32_t max_pairs, const uint32_t* __restrict__ t
     }
     __syncthreads();
     for (int t = tid; t < ntiles; t += 1024) {
-        const uint32_t pos = atomicAdd(&bucket_pos[size_bucket(tile_count[t])], 1u);
+        uint32_t v = 0;
+#pragma unroll
+        for (int c = 0; c < GSR_COPIES; ++c) v += tile_count[(size_t)c * ntiles + t];
+        const uint32_t pos = atomicAdd(&bucket_pos[size_bucket(v)], 1u);
         work_order[pos] = (uint32_t)t;
     }
 }
@@ -103,7 +120,7 @@ scan_order_kernel(int ntiles, uint32_t max_pairs, const uint32_t* __restrict__ t
 // scatter: one Gaussian per thread appends its key to every touched tile
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-scatter_kernel(int P, int gx, uint32_t max_pairs, const uint4* __restrict__ rectdepth,
+scatter_kernel(int P, int gx, int ntiles, uint32_t max_pairs, const uint4* __restrict__ rectdepth,
                uint32_t* __restrict__ tile_cursor, unsigned long long* __restrict__ keys) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
@@ -111,50 +128,142 @@ scatter_kernel(int P, int gx, uint32_t max_pairs, const uint4* __restrict__ rect
     if (rd.w == 0) return;
     const int minx = rd.x & 0xffff, miny = rd.x >> 16, maxx = rd.y & 0xffff, maxy = rd.y >> 16;
     const unsigned long long key = ((unsigned long long)rd.z << 32) | (uint32_t)i;
+    uint32_t* cur = tile_cursor + (size_t)((i >> 5) & (GSR_COPIES - 1)) * ntiles;
     for (int ty = miny; ty < maxy; ++ty)
         for (int tx = minx; tx < maxx; ++tx) {
-            const uint32_t pos = atomicAdd(tile_cursor + ty * gx + tx, 1u);
+            const uint32_t pos = atomicAdd(cur + ty * gx + tx, 1u);
             if (pos < max_pairs) keys[pos] = key;
         }
 }
 
 // ---------------------------------------------------------------------------------------------
-// bitonic network (flip variant: every comparator leaves the minimum at the lower index, so
-// virtual +inf padding above n needs no storage: comparators reaching past n are no-ops)
+// In-smem LSD radix sort of n <= NT*ITEMS 64-bit keys on their HIGH 32 bits (depth), followed by a
+// pass that orders runs of equal depth by the low 32 bits (Gaussian index).
+// Element order is warp-major: warp w owns rows j = 0..rows-1 of 32 consecutive elements
+//   e(w, j, lane) = (w*rows + j)*32 + lane.
+// Per pass: (1) per-warp digit histogram, (2) scan over (digit, warp), (3) stable re-rank with
+// ballot-derived peer masks and scatter into the smem buffer, (4) read back into registers.
 // ---------------------------------------------------------------------------------------------
-template <int NT>
-__device__ __forceinline__ void bitonic_smem(unsigned long long* s, int n, int k_begin, int k_end,
-                                             int j_first_limit) {
-    // runs merge sizes k = k_begin .. k_end (powers of two); for each k the steps with
-    // distance < j_first_limit only (used by the out-of-core path); normally j_first_limit = inf
-    for (int k = k_begin; k <= k_end; k <<= 1) {
-        const int half = k >> 1;
-        if (half < j_first_limit) {
-            // flip step: i = b*k + off, l = b*k + k-1-off
-            for (int t = threadIdx.x; ; t += NT) {
-                const int b = t / half, off = t - b * half;
-                const int i = b * k + off, l = b * k + k - 1 - off;
-                if (i >= n) break;
-                if (l < n) {
-                    const unsigned long long a = s[i], c = s[l];
-                    if (a > c) { s[i] = c; s[l] = a; }
+template <int NT, int ITEMS>
+__device__ __forceinline__ void radix_sort_smem(unsigned long long* s, uint32_t* hist /*[NT/32][256]*/,
+                                                uint32_t* digit_base /*[256]*/, uint32_t* red /*[2]*/,
+                                                int n) {
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int rows = (n + NW * 32 - 1) / (NW * 32);   // rows per warp actually used (<= ITEMS)
+    unsigned long long k[ITEMS];
+    uint32_t vor = 0u, vand = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const int e = (w * rows + j) * 32 + lane;
+        const bool ok = j < rows && e < n;
+        k[j] = ok ? s[e] : ~0ull;
+        if (ok) { vor |= (uint32_t)(k[j] >> 32); vand &= (uint32_t)(k[j] >> 32); }
+    }
+    vor = __reduce_or_sync(0xffffffffu, vor);
+    vand = __reduce_and_sync(0xffffffffu, vand);
+    if (tid == 0) { red[0] = 0u; red[1] = 0xffffffffu; }
+    __syncthreads();
+    if (lane == 0) { atomicOr(&red[0], vor); atomicAnd(&red[1], vand); }
+    __syncthreads();
+    const uint32_t varying = red[0] ^ red[1];   // depth bits that differ somewhere in the list
+
+#pragma unroll 1
+    for (int shift = 32; shift < 64; shift += 8) {
+        if (((varying >> (shift - 32)) & 0xffu) == 0u) continue;   // constant digit: pass is a no-op
+        // (1) per-warp histogram
+        for (int d = lane; d < 256; d += 32) hist[w * 256 + d] = 0u;
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            if (j < rows) {
+                const uint32_t dg = (uint32_t)(k[j] >> shift) & 0xffu;
+                uint32_t peers = 0xffffffffu;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const uint32_t v = __ballot_sync(0xffffffffu, (dg >> b) & 1u);
+                    peers &= ((dg >> b) & 1u) ? v : ~v;
                 }
+                if ((peers & lt_mask) == 0u) hist[w * 256 + dg] += __popc(peers);   // group leader
+                __syncwarp();
             }
-            __syncthreads();
         }
-        for (int j = half >> 1; j > 0; j >>= 1) {
-            if (j >= j_first_limit) continue;
-            for (int t = threadIdx.x; ; t += NT) {
-                const int i = 2 * j * (t / j) + (t % j), l = i + j;
-                if (i >= n) break;
-                if (l < n) {
-                    const unsigned long long a = s[i], c = s[l];
-                    if (a > c) { s[i] = c; s[l] = a; }
-                }
+        __syncthreads();
+        // (2) scan: for every digit, exclusive prefix over warps; then exclusive prefix over digits
+        if (tid < 256) {
+            uint32_t run = 0;
+#pragma unroll 4
+            for (int ww = 0; ww < NW; ++ww) {
+                const uint32_t c = hist[ww * 256 + tid];
+                hist[ww * 256 + tid] = run;
+                run += c;
             }
-            __syncthreads();
+            // exclusive scan of `run` over the 256 digit threads (8 warps)
+            uint32_t incl = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) digit_base[256 + w] = incl;   // per-warp totals (8 entries)
+            __syncwarp();
+            // all 8 warps see each other's totals only after a barrier: use named barrier 1 (256 thr)
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            uint32_t wbase = 0;
+            for (int ww = 0; ww < w; ++ww) wbase += digit_base[256 + ww];
+            digit_base[tid] = wbase + incl - run;
+        }
+        __syncthreads();
+        // (3) stable rank + scatter (keys are in registers, so the buffer can be overwritten)
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            if (j < rows) {
+                const uint32_t dg = (uint32_t)(k[j] >> shift) & 0xffu;
+                uint32_t peers = 0xffffffffu;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const uint32_t v = __ballot_sync(0xffffffffu, (dg >> b) & 1u);
+                    peers &= ((dg >> b) & 1u) ? v : ~v;
+                }
+                const int leader = __ffs(peers) - 1;
+                uint32_t base = 0;
+                if (lane == leader) {
+                    base = hist[w * 256 + dg];
+                    hist[w * 256 + dg] = base + __popc(peers);
+                }
+                base = __shfl_sync(0xffffffffu, base, leader);
+                const uint32_t dst = digit_base[dg] + base + __popc(peers & lt_mask);
+                if (dst < (uint32_t)n) s[dst] = k[j];   // padding keys (all ones) rank last: dropped
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // (4) back to registers in warp-major order
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const int e = (w * rows + j) * 32 + lane;
+            k[j] = (j < rows && e < n) ? s[e] : ~0ull;
+        }
+        __syncthreads();
+    }
+    // tie pass: runs of equal depth bits are ordered by index (arrival order was arbitrary)
+    for (int i = tid; i < n; i += NT) {
+        const uint32_t d = (uint32_t)(s[i] >> 32);
+        const bool head = (i == 0 || (uint32_t)(s[i - 1] >> 32) != d) && (i + 1 < n) &&
+                          (uint32_t)(s[i + 1] >> 32) == d;
+        if (head) {
+            int e = i + 1;
+            while (e < n && (uint32_t)(s[e] >> 32) == d) ++e;
+            for (int a = i + 1; a < e; ++a) {          // insertion sort of s[i, e)
+                const unsigned long long x = s[a];
+                int b = a - 1;
+                while (b >= i && s[b] > x) { s[b + 1] = s[b]; --b; }
+                s[b + 1] = x;
+            }
         }
     }
+    __syncthreads();
 }
 
 __device__ __forceinline__ int next_pow2(int n) {
@@ -175,15 +284,28 @@ __device__ __forceinline__ void gather_records(const unsigned long long* keys_so
     }
 }
 
-// small tiles: n <= 4096 keys entirely in 32 KB of shared memory, 256 threads
+struct SortSmemSmall {
+    unsigned long long keys[GSR_SORT_SMALL_MAX];
+    uint32_t hist[8 * 256];
+    uint32_t digit_base[256 + 8];
+    uint32_t red[2];
+};
+struct SortSmemBig {
+    unsigned long long keys[GSR_SORT_BIG_CHUNK];
+    uint32_t hist[32 * 256];
+    uint32_t digit_base[256 + 8];
+    uint32_t red[2];
+};
+
+// small tiles: n <= 4096, 256 threads x 16 items
 __global__ void __launch_bounds__(256)
 sort_small_kernel(const uint32_t* __restrict__ header, const uint32_t* __restrict__ work_order,
-                  const uint32_t* __restrict__ tile_start, unsigned long long* __restrict__ keys,
+                  const uint32_t* __restrict__ tile_start, const unsigned long long* __restrict__ keys,
                   const GsrRec* __restrict__ geom, GsrRec* __restrict__ records) {
-    __shared__ unsigned long long s[GSR_SORT_SMALL_MAX];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SortSmemSmall& sm = *reinterpret_cast<SortSmemSmall*>(smem_raw);
     const uint32_t max_pairs = header[GSR_H_MAX_PAIRS];
     const uint32_t nonempty = header[GSR_H_NUM_NONEMPTY];
-    // tiles [0, NUM_BIG) may hold > 4096 keys; those exactly at 4096 are handled here too
     for (uint32_t w = blockIdx.x; w < nonempty; w += gridDim.x) {
         const uint32_t tile = work_order[w];
         uint32_t beg = tile_start[tile], end = tile_start[tile + 1];
@@ -191,22 +313,24 @@ sort_small_kernel(const uint32_t* __restrict__ header, const uint32_t* __restric
         if (end > max_pairs) end = max_pairs;                  // overflow: stay in bounds
         if (beg >= end) continue;
         const int n = (int)(end - beg);
-        for (int i = threadIdx.x; i < n; i += 256) s[i] = keys[beg + i];
+        for (int i = threadIdx.x; i < n; i += 256) sm.keys[i] = keys[beg + i];
         __syncthreads();
-        bitonic_smem<256>(s, n, 2, next_pow2(n), 1 << 30);
-        gather_records<256, false>(s, n, geom, records + beg);
+        radix_sort_smem<256, 16>(sm.keys, sm.hist, sm.digit_base, sm.red, n);
+        gather_records<256, false>(sm.keys, n, geom, records + beg);
         __syncthreads();
     }
 }
 
-// big tiles: 1024 threads; up to 16384 keys in 128 KB smem; beyond that a hierarchical
-// (out-of-core) bitonic sort working in place on the global key segment.
+// big tiles: 1024 threads x 8 items per 8192-key chunk; lists longer than one chunk are sorted
+// chunk by chunk (radix) and merged in place in global memory with bitonic merge steps.
 __global__ void __launch_bounds__(1024)
 sort_big_kernel(const uint32_t* __restrict__ header, const uint32_t* __restrict__ work_order,
                 const uint32_t* __restrict__ tile_start, unsigned long long* __restrict__ keys,
                 const GsrRec* __restrict__ geom, GsrRec* __restrict__ records) {
-    extern __shared__ __align__(16) unsigned long long sb[];
-    constexpr int CH = GSR_SORT_BIG_SMEM;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SortSmemBig& sm = *reinterpret_cast<SortSmemBig*>(smem_raw);
+    unsigned long long* sb = sm.keys;
+    constexpr int CH = GSR_SORT_BIG_CHUNK;
     const uint32_t max_pairs = header[GSR_H_MAX_PAIRS];
     const uint32_t nbig = header[GSR_H_NUM_BIG];
     for (uint32_t w = blockIdx.x; w < nbig; w += gridDim.x) {
@@ -220,25 +344,26 @@ sort_big_kernel(const uint32_t* __restrict__ header, const uint32_t* __restrict_
         if (n <= CH) {
             for (int i = threadIdx.x; i < n; i += 1024) sb[i] = gk[i];
             __syncthreads();
-            bitonic_smem<1024>(sb, n, 2, next_pow2(n), 1 << 30);
+            radix_sort_smem<1024, 8>(sb, sm.hist, sm.digit_base, sm.red, n);
             gather_records<1024, false>(sb, n, geom, records + beg);
             __syncthreads();
             continue;
         }
-        // ---- out-of-core: sort CH-sized chunks, then merge with global + shared steps ------
+        // ---- longer than one chunk: radix-sort CH-sized chunks, then bitonic merges ---------
         const int N = next_pow2(n);
         for (int c0 = 0; c0 < n; c0 += CH) {
             const int m = min(CH, n - c0);
-            for (int i = threadIdx.x; i < m; i += 1024) sb[i] = gk[c0 + i];
+            for (int i = threadIdx.x; i < m; i += 1024) sb[i] = __ldcg(gk + c0 + i);
             __syncthreads();
-            bitonic_smem<1024>(sb, m, 2, CH, 1 << 30);
-            for (int i = threadIdx.x; i < m; i += 1024) gk[c0 + i] = sb[i];
+            radix_sort_smem<1024, 8>(sb, sm.hist, sm.digit_base, sm.red, m);
+            for (int i = threadIdx.x; i < m; i += 1024) __stcg(gk + c0 + i, sb[i]);
             __syncthreads();
         }
+        // flip-variant bitonic merge network: every comparator leaves the minimum at the lower
+        // index, so the virtual +inf padding above n needs no storage (such comparators are no-ops)
         for (int k = 2 * CH; k <= N; k <<= 1) {
             const int half = k >> 1;
-            // flip step in global memory (distance up to k-1 >= CH)
-            for (int t = threadIdx.x; t < N / 2; t += 1024) {
+            for (int t = threadIdx.x; t < N / 2; t += 1024) {          // flip step (global)
                 const int b = t / half, off = t - b * half;
                 const int i = b * k + off, l = b * k + k - 1 - off;
                 if (i < n && l < n) {
@@ -247,7 +372,7 @@ sort_big_kernel(const uint32_t* __restrict__ header, const uint32_t* __restrict_
                 }
             }
             __syncthreads();
-            for (int j = half >> 1; j >= CH; j >>= 1) {
+            for (int j = half >> 1; j >= CH; j >>= 1) {                 // half cleaners (global)
                 for (int t = threadIdx.x; t < N / 2; t += 1024) {
                     const int i = 2 * j * (t / j) + (t % j), l = i + j;
                     if (i < n && l < n) {
@@ -257,8 +382,7 @@ sort_big_kernel(const uint32_t* __restrict__ header, const uint32_t* __restrict_
                 }
                 __syncthreads();
             }
-            // remaining distances < CH: independent inside every CH chunk -> shared memory
-            for (int c0 = 0; c0 < n; c0 += CH) {
+            for (int c0 = 0; c0 < n; c0 += CH) {                        // distances < CH: in smem
                 const int m = min(CH, n - c0);
                 for (int i = threadIdx.x; i < m; i += 1024) sb[i] = __ldcg(gk + c0 + i);
                 __syncthreads();
@@ -283,43 +407,65 @@ sort_big_kernel(const uint32_t* __restrict__ header, const uint32_t* __restrict_
     }
 }
 
+struct BinPtrs {
+    GsrTileGrid grid;
+    uint32_t *header, *tile_start, *work_order, *tile_count, *tile_cursor;
+    GsrRec* records;
+    unsigned long long* keys;
+    const GsrRec* geom;
+    const uint4* rectdepth;
+};
+BinPtrs bin_ptrs(const GsrFwdArgs& a) {
+    BinPtrs b;
+    b.grid = gsr_grid(a.prm.image_height, a.prm.image_width);
+    b.header = reinterpret_cast<uint32_t*>(a.saved + a.vl.header);
+    b.tile_start = reinterpret_cast<uint32_t*>(a.saved + a.vl.tile_start);
+    b.work_order = reinterpret_cast<uint32_t*>(a.saved + a.vl.work_order);
+    b.records = reinterpret_cast<GsrRec*>(a.saved + a.vl.records);
+    b.tile_count = reinterpret_cast<uint32_t*>(a.scratch + a.sl.tile_count);
+    b.tile_cursor = reinterpret_cast<uint32_t*>(a.scratch + a.sl.tile_cursor);
+    b.keys = reinterpret_cast<unsigned long long*>(a.scratch + a.sl.keys);
+    b.geom = reinterpret_cast<const GsrRec*>(a.scratch + a.sl.geom);
+    b.rectdepth = reinterpret_cast<const uint4*>(a.scratch + a.sl.rectdepth);
+    return b;
+}
 }  // namespace
 
-cudaError_t gsr_launch_binning(const GsrFwdArgs& a) {
-    const GsrTileGrid grid = gsr_grid(a.prm.image_height, a.prm.image_width);
-    uint32_t* header = reinterpret_cast<uint32_t*>(a.saved + a.vl.header);
-    uint32_t* tile_start = reinterpret_cast<uint32_t*>(a.saved + a.vl.tile_start);
-    uint32_t* work_order = reinterpret_cast<uint32_t*>(a.saved + a.vl.work_order);
-    GsrRec* records = reinterpret_cast<GsrRec*>(a.saved + a.vl.records);
-    uint32_t* tile_count = reinterpret_cast<uint32_t*>(a.scratch + a.sl.tile_count);
-    uint32_t* tile_cursor = reinterpret_cast<uint32_t*>(a.scratch + a.sl.tile_cursor);
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(a.scratch + a.sl.keys);
-    const GsrRec* geom = reinterpret_cast<const GsrRec*>(a.scratch + a.sl.geom);
-    const uint4* rectdepth = reinterpret_cast<const uint4*>(a.scratch + a.sl.rectdepth);
-
-    scan_order_kernel<<<1, 1024, 0, a.stream>>>(grid.ntiles, a.max_pairs, tile_count, tile_start,
-                                                 tile_cursor, work_order, header, a.host_notify,
+cudaError_t gsr_launch_scan(const GsrFwdArgs& a) {
+    const BinPtrs b = bin_ptrs(a);
+    scan_order_kernel<<<1, 1024, 0, a.stream>>>(b.grid.ntiles, a.max_pairs, b.tile_count, b.tile_start,
+                                                 b.tile_cursor, b.work_order, b.header, a.host_notify,
                                                  a.notify_seq);
+    return cudaGetLastError();
+}
+
+cudaError_t gsr_launch_scatter(const GsrFwdArgs& a) {
+    const BinPtrs b = bin_ptrs(a);
     if (a.prm.P > 0)
-        scatter_kernel<<<(a.prm.P + 255) / 256, 256, 0, a.stream>>>(a.prm.P, grid.gx, a.max_pairs,
-                                                                     rectdepth, tile_cursor, keys);
-    const int big_smem = GSR_SORT_BIG_SMEM * 8;
-    {
-        cudaError_t e = cudaFuncSetAttribute(sort_big_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem);
-        if (e != cudaSuccess) return e;
-    }
+        scatter_kernel<<<(a.prm.P + 255) / 256, 256, 0, a.stream>>>(a.prm.P, b.grid.gx, b.grid.ntiles,
+                                                                     a.max_pairs, b.rectdepth, b.tile_cursor,
+                                                                     b.keys);
+    return cudaGetLastError();
+}
+
+cudaError_t gsr_launch_sort(const GsrFwdArgs& a) {
+    const BinPtrs b = bin_ptrs(a);
+    const int big_smem = (int)sizeof(SortSmemBig), small_smem = (int)sizeof(SortSmemSmall);
+    cudaError_t e = cudaFuncSetAttribute(sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(sort_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem);
+    if (e != cudaSuccess) return e;
     int nsm = 148;
     {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     }
-    const int small_grid = min(grid.ntiles, nsm * 6);
-    const int big_grid = min(grid.ntiles, nsm);
-    sort_big_kernel<<<big_grid, 1024, big_smem, a.stream>>>(header, work_order, tile_start, keys, geom,
-                                                            records);
-    sort_small_kernel<<<small_grid, 256, 0, a.stream>>>(header, work_order, tile_start, keys, geom,
-                                                        records);
+    const int small_grid = min(b.grid.ntiles, nsm * 4);
+    const int big_grid = min(b.grid.ntiles, nsm * 2);
+    sort_big_kernel<<<big_grid, 1024, big_smem, a.stream>>>(b.header, b.work_order, b.tile_start, b.keys,
+                                                            b.geom, b.records);
+    sort_small_kernel<<<small_grid, 256, small_smem, a.stream>>>(b.header, b.work_order, b.tile_start, b.keys,
+                                                                 b.geom, b.records);
     return cudaGetLastError();
 }

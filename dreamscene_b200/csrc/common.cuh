@@ -51,8 +51,11 @@ enum { GSR_H_NUM_PAIRS = 0, GSR_H_MAX_PAIRS = 1, GSR_H_NUM_TILES = 2, GSR_H_OVER
 // counters in scratch
 enum { GSR_C_FWD_QUEUE = 0, GSR_C_BWD_QUEUE = 1, GSR_C_SORT_SMALL = 2, GSR_C_SORT_BIG = 3 };
 
-#define GSR_SORT_SMALL_MAX 4096   // keys sorted by the 256-thread kernel (32 KB smem)
-#define GSR_SORT_BIG_SMEM 16384   // keys per smem chunk of the 1024-thread kernel (128 KB)
+#define GSR_SORT_SMALL_MAX 4096   // keys sorted by the 256-thread kernel (256 x 16 items)
+#define GSR_SORT_BIG_CHUNK 8192   // keys per smem chunk of the 1024-thread kernel (1024 x 8 items)
+// Tile counters/cursors are privatised into GSR_COPIES arrays (copy = (gaussian_idx>>5) & mask):
+// same-address L2 atomics serialise at ~30 ns each, so the hottest tile bounds the kernel.
+#define GSR_COPIES 16
 
 #ifdef __CUDACC__
 // ---- 128-bit global access helpers -------------------------------------------------------
@@ -152,7 +155,9 @@ struct GsrBwdArgs {
 };
 
 cudaError_t gsr_launch_project(const GsrFwdArgs& a);
-cudaError_t gsr_launch_binning(const GsrFwdArgs& a);       // scan + order + scatter + sort
+cudaError_t gsr_launch_scan(const GsrFwdArgs& a);          // exclusive scan + work order + host notify
+cudaError_t gsr_launch_scatter(const GsrFwdArgs& a);       // append keys to tile lists
+cudaError_t gsr_launch_sort(const GsrFwdArgs& a);          // per-tile sort + record gather (2 kernels)
 cudaError_t gsr_launch_composite_fwd(const GsrFwdArgs& a);
 cudaError_t gsr_launch_composite_bwd(const GsrBwdArgs& a);
 cudaError_t gsr_launch_project_bwd(const GsrBwdArgs& a);

@@ -294,8 +294,9 @@ project_sh_kernel(b200gsr_params p, const float* __restrict__ means3D,
                 const float4* src = reinterpret_cast<const float4*>(&rec);
                 dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
 
+                uint32_t* cnt = tile_count + (size_t)((i >> 5) & (GSR_COPIES - 1)) * grid.ntiles;
                 for (int ty = miny; ty < maxy; ++ty)
-                    for (int tx = minx; tx < maxx; ++tx) atomicAdd(tile_count + ty * grid.gx + tx, 1u);
+                    for (int tx = minx; tx < maxx; ++tx) atomicAdd(cnt + ty * grid.gx + tx, 1u);
             }
         }
     }

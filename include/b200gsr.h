@@ -77,8 +77,8 @@ typedef struct b200gsr_saved_layout {
 /* Byte offsets inside the transient `scratch` buffer (valid until the next call on the stream). */
 typedef struct b200gsr_scratch_layout {
     size_t counters;      /* uint32[16] work-queue counters */
-    size_t tile_count;    /* uint32[num_tiles] */
-    size_t tile_cursor;   /* uint32[num_tiles] */
+    size_t tile_count;    /* uint32[16][num_tiles] privatised per-tile pair counters */
+    size_t tile_cursor;   /* uint32[16][num_tiles] write cursors */
     size_t rectdepth;     /* uint4[P]: (minx|miny<<16, maxx|maxy<<16, depth bits, tiles touched) */
     size_t geom;          /* 48-byte records [P] in Gaussian order */
     size_t keys;          /* uint64[max_pairs] (depth_bits<<32 | idx), tile-major, unsorted->sorted */
@@ -138,6 +138,19 @@ int b200gsr_backward(const b200gsr_params* prm,
 /* Frustum test only (replaces _C.mark_visible; DreamScene never calls it): visible[P] bytes. */
 int b200gsr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
                          const float* projmatrix, uint8_t* visible, void* stream);
+
+/*
+ * Optional per-stage device timing for benchmarks (no upstream equivalent).  Process-wide and not
+ * thread-safe.  enable(max_calls>0) allocates CUDA events; every later forward/backward call
+ * (up to max_calls each) records events around its stages on the call's stream; read() waits for
+ * that call and returns elapsed milliseconds:
+ *   forward  ms[5] = {project_sh, scan_order, scatter, tile_sort(2 kernels), composite_fwd}
+ *   backward ms[2] = {composite_bwd, project_bwd}
+ * enable(0) frees everything.
+ */
+int b200gsr_profile_enable(int32_t max_calls);
+int b200gsr_profile_counts(int32_t* n_forward, int32_t* n_backward);
+int b200gsr_profile_read(int32_t is_backward, int32_t call, float* ms);
 
 #ifdef __cplusplus
 }
