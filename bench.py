@@ -42,7 +42,7 @@ WORKLOADS = {
     "cfg1_10k_256": dict(P=10_000, H=256, W=256, radius=0.5, opacity="sigmoid_normal"),
 }
 METRIC = "fwd+bwd Mpix/s @1M Gaussians/1024^2"
-KERNELS_PER_STEP = 8   # project_sh, scan_order, scatter, sort_big, sort_small, composite_fwd, composite_bwd, project_bwd
+KERNELS_PER_STEP = 9   # project_sh, scan_order, scatter, sort_big, sort_small, gather_records, composite_fwd, composite_bwd, project_bwd
 
 
 def measured_peaks():
@@ -209,7 +209,7 @@ def algorithmic_bytes(P, V, D, N, M):
         "project_sh": P * g_in + P * (4 + 16) + V * 48,        # params; radii + rect/depth; geom record
         "scan_order": 0,
         "scatter": P * 16 + D * 8,                               # rect/depth read; key write
-        "tile_sort": D * 8 + D * 48 + D * 48,                    # key read; record gather; record write
+        "tile_sort": D * 8 * 2 + D * 8 + D * 48 + D * 48,        # key read+write (sort); key read, record gather, record write
         "composite_fwd": D * 48 + N * (12 + 8 + 4),              # records; colour, depth_alpha, n_contrib
         "composite_bwd": D * 48 + N * (20 + 8) + V * 48,         # records; grads in + T/n_contrib; dgeom
         "project_bwd": P * g_in + V * 48 + P * 4 + P * (g_in + 12),  # params, dgeom, radii; grads out

@@ -11,10 +11,10 @@
 //   sort kernels      : ... and is then fixed by sorting each tile's keys on (depth bits, idx):
 //                       identical to a stable sort of (tile<<32 | depth bits) over pairs emitted
 //                       in Gaussian-index order, i.e. bit-exact with the oracle's lists.
-//                       In-smem LSD radix sort (8-bit digits, ballot ranking, constant digit
+//                       In-smem LSD radix sort (8-bit digits, match.any ranking, constant digit
 //                       bytes skipped) on the depth bits + a tie pass ordering equal depths by
 //                       index; lists longer than one chunk are merged with bitonic merge steps.
-//                       Epilogue gathers the 48-B record of every entry into the tile-major,
+//   gather_records    : expands every sorted entry into its 48-B record -> the tile-major,
 //                       depth-sorted record array the composite kernels stream with TMA.
 #include "common.cuh"
 
@@ -142,7 +142,7 @@ scatter_kernel(int P, int gx, int ntiles, uint32_t max_pairs, const uint4* __res
 // Element order is warp-major: warp w owns rows j = 0..rows-1 of 32 consecutive elements
 //   e(w, j, lane) = (w*rows + j)*32 + lane.
 // Per pass: (1) per-warp digit histogram, (2) scan over (digit, warp), (3) stable re-rank with
-// ballot-derived peer masks and scatter into the smem buffer, (4) read back into registers.
+// match.any peer masks and scatter into the smem buffer, (4) read back into registers.
 // ---------------------------------------------------------------------------------------------
 template <int NT, int ITEMS>
 __device__ __forceinline__ void radix_sort_smem(unsigned long long* s, uint32_t* hist /*[NT/32][256]*/,
@@ -172,23 +172,12 @@ __device__ __forceinline__ void radix_sort_smem(unsigned long long* s, uint32_t*
 #pragma unroll 1
     for (int shift = 32; shift < 64; shift += 8) {
         if (((varying >> (shift - 32)) & 0xffu) == 0u) continue;   // constant digit: pass is a no-op
-        // (1) per-warp histogram
+        // (1) per-warp histogram (native 32-bit shared-memory atomics)
         for (int d = lane; d < 256; d += 32) hist[w * 256 + d] = 0u;
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            if (j < rows) {
-                const uint32_t dg = (uint32_t)(k[j] >> shift) & 0xffu;
-                uint32_t peers = 0xffffffffu;
-#pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    const uint32_t v = __ballot_sync(0xffffffffu, (dg >> b) & 1u);
-                    peers &= ((dg >> b) & 1u) ? v : ~v;
-                }
-                if ((peers & lt_mask) == 0u) hist[w * 256 + dg] += __popc(peers);   // group leader
-                __syncwarp();
-            }
-        }
+        for (int j = 0; j < ITEMS; ++j)
+            if (j < rows) atomicAdd(&hist[w * 256 + ((uint32_t)(k[j] >> shift) & 0xffu)], 1u);
         __syncthreads();
         // (2) scan: for every digit, exclusive prefix over warps; then exclusive prefix over digits
         if (tid < 256) {
@@ -220,12 +209,7 @@ __device__ __forceinline__ void radix_sort_smem(unsigned long long* s, uint32_t*
         for (int j = 0; j < ITEMS; ++j) {
             if (j < rows) {
                 const uint32_t dg = (uint32_t)(k[j] >> shift) & 0xffu;
-                uint32_t peers = 0xffffffffu;
-#pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    const uint32_t v = __ballot_sync(0xffffffffu, (dg >> b) & 1u);
-                    peers &= ((dg >> b) & 1u) ? v : ~v;
-                }
+                const uint32_t peers = __match_any_sync(0xffffffffu, dg);   // lanes holding the same digit
                 const int leader = __ffs(peers) - 1;
                 uint32_t base = 0;
                 if (lane == leader) {
@@ -270,17 +254,20 @@ __device__ __forceinline__ int next_pow2(int n) {
     return n <= 1 ? 1 : 1 << (32 - __clz(n - 1));
 }
 
-// copy geom[idx] records into the sorted array: 3 lanes per record, one 16-B part each
-template <int NT, bool GLOBAL_KEYS>
-__device__ __forceinline__ void gather_records(const unsigned long long* keys_sorted, int n,
-                                               const GsrRec* __restrict__ geom,
-                                               GsrRec* __restrict__ out) {
+// Record expansion: sorted[pos] = geom[idx(keys[pos])], one 16-B part per thread (3 per record).
+// Purely memory bound (random 48-B reads that mostly hit L2, streaming writes).
+__global__ void __launch_bounds__(256)
+gather_records_kernel(const uint32_t* __restrict__ header, const unsigned long long* __restrict__ keys,
+                      const GsrRec* __restrict__ geom, GsrRec* __restrict__ records) {
+    const uint32_t n = min(header[GSR_H_NUM_PAIRS], header[GSR_H_MAX_PAIRS]);
     const float4* g4 = reinterpret_cast<const float4*>(geom);
-    float4* o4 = reinterpret_cast<float4*>(out);
-    for (int j = threadIdx.x; j < 3 * n; j += NT) {
-        const int r = j / 3, part = j - 3 * r;
-        const uint32_t idx = GLOBAL_KEYS ? (uint32_t)__ldcg(keys_sorted + r) : (uint32_t)keys_sorted[r];
-        o4[j] = __ldg(g4 + 3 * (size_t)idx + part);
+    float4* o4 = reinterpret_cast<float4*>(records);
+    const size_t total = 3 * (size_t)n, step = (size_t)gridDim.x * blockDim.x;
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += step) {
+        const size_t r = j / 3;
+        const uint32_t part = (uint32_t)(j - 3 * r);
+        const uint32_t idx = (uint32_t)__ldg(keys + r);
+        stg_na_f4(o4 + j, __ldg(g4 + 3 * (size_t)idx + part));
     }
 }
 
@@ -300,8 +287,7 @@ struct SortSmemBig {
 // small tiles: n <= 4096, 256 threads x 16 items
 __global__ void __launch_bounds__(256)
 sort_small_kernel(const uint32_t* __restrict__ header, const uint32_t* __restrict__ work_order,
-                  const uint32_t* __restrict__ tile_start, const unsigned long long* __restrict__ keys,
-                  const GsrRec* __restrict__ geom, GsrRec* __restrict__ records) {
+                  const uint32_t* __restrict__ tile_start, unsigned long long* __restrict__ keys) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SortSmemSmall& sm = *reinterpret_cast<SortSmemSmall*>(smem_raw);
     const uint32_t max_pairs = header[GSR_H_MAX_PAIRS];
@@ -316,7 +302,7 @@ sort_small_kernel(const uint32_t* __restrict__ header, const uint32_t* __restric
         for (int i = threadIdx.x; i < n; i += 256) sm.keys[i] = keys[beg + i];
         __syncthreads();
         radix_sort_smem<256, 16>(sm.keys, sm.hist, sm.digit_base, sm.red, n);
-        gather_records<256, false>(sm.keys, n, geom, records + beg);
+        for (int i = threadIdx.x; i < n; i += 256) keys[beg + i] = sm.keys[i];
         __syncthreads();
     }
 }
@@ -325,8 +311,7 @@ sort_small_kernel(const uint32_t* __restrict__ header, const uint32_t* __restric
 // chunk by chunk (radix) and merged in place in global memory with bitonic merge steps.
 __global__ void __launch_bounds__(1024)
 sort_big_kernel(const uint32_t* __restrict__ header, const uint32_t* __restrict__ work_order,
-                const uint32_t* __restrict__ tile_start, unsigned long long* __restrict__ keys,
-                const GsrRec* __restrict__ geom, GsrRec* __restrict__ records) {
+                const uint32_t* __restrict__ tile_start, unsigned long long* __restrict__ keys) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SortSmemBig& sm = *reinterpret_cast<SortSmemBig*>(smem_raw);
     unsigned long long* sb = sm.keys;
@@ -344,8 +329,8 @@ sort_big_kernel(const uint32_t* __restrict__ header, const uint32_t* __restrict_
         if (n <= CH) {
             for (int i = threadIdx.x; i < n; i += 1024) sb[i] = gk[i];
             __syncthreads();
-            radix_sort_smem<1024, 8>(sb, sm.hist, sm.digit_base, sm.red, n);
-            gather_records<1024, false>(sb, n, geom, records + beg);
+            radix_sort_smem<1024, 16>(sb, sm.hist, sm.digit_base, sm.red, n);
+            for (int i = threadIdx.x; i < n; i += 1024) gk[i] = sb[i];
             __syncthreads();
             continue;
         }
@@ -355,16 +340,16 @@ sort_big_kernel(const uint32_t* __restrict__ header, const uint32_t* __restrict_
             const int m = min(CH, n - c0);
             for (int i = threadIdx.x; i < m; i += 1024) sb[i] = __ldcg(gk + c0 + i);
             __syncthreads();
-            radix_sort_smem<1024, 8>(sb, sm.hist, sm.digit_base, sm.red, m);
+            radix_sort_smem<1024, 16>(sb, sm.hist, sm.digit_base, sm.red, m);
             for (int i = threadIdx.x; i < m; i += 1024) __stcg(gk + c0 + i, sb[i]);
             __syncthreads();
         }
         // flip-variant bitonic merge network: every comparator leaves the minimum at the lower
         // index, so the virtual +inf padding above n needs no storage (such comparators are no-ops)
         for (int k = 2 * CH; k <= N; k <<= 1) {
-            const int half = k >> 1;
+            const int half = k >> 1, lhalf = 31 - __clz(half);
             for (int t = threadIdx.x; t < N / 2; t += 1024) {          // flip step (global)
-                const int b = t / half, off = t - b * half;
+                const int b = t >> lhalf, off = t - b * half;
                 const int i = b * k + off, l = b * k + k - 1 - off;
                 if (i < n && l < n) {
                     const unsigned long long a = __ldcg(gk + i), c = __ldcg(gk + l);
@@ -373,8 +358,9 @@ sort_big_kernel(const uint32_t* __restrict__ header, const uint32_t* __restrict_
             }
             __syncthreads();
             for (int j = half >> 1; j >= CH; j >>= 1) {                 // half cleaners (global)
+                const int lj = 31 - __clz(j);
                 for (int t = threadIdx.x; t < N / 2; t += 1024) {
-                    const int i = 2 * j * (t / j) + (t % j), l = i + j;
+                    const int i = ((t >> lj) << (lj + 1)) + (t & (j - 1)), l = i + j;
                     if (i < n && l < n) {
                         const unsigned long long a = __ldcg(gk + i), c = __ldcg(gk + l);
                         if (a > c) { __stcg(gk + i, c); __stcg(gk + l, a); }
@@ -387,8 +373,9 @@ sort_big_kernel(const uint32_t* __restrict__ header, const uint32_t* __restrict_
                 for (int i = threadIdx.x; i < m; i += 1024) sb[i] = __ldcg(gk + c0 + i);
                 __syncthreads();
                 for (int j = CH >> 1; j > 0; j >>= 1) {
+                    const int lj = 31 - __clz(j);
                     for (int t = threadIdx.x; ; t += 1024) {
-                        const int i = 2 * j * (t / j) + (t % j), l = i + j;
+                        const int i = ((t >> lj) << (lj + 1)) + (t & (j - 1)), l = i + j;
                         if (i >= m) break;
                         if (l < m) {
                             const unsigned long long a = sb[i], c = sb[l];
@@ -401,9 +388,6 @@ sort_big_kernel(const uint32_t* __restrict__ header, const uint32_t* __restrict_
                 __syncthreads();
             }
         }
-        __threadfence_block();
-        gather_records<1024, true>(gk, n, geom, records + beg);
-        __syncthreads();
     }
 }
 
@@ -462,10 +446,9 @@ cudaError_t gsr_launch_sort(const GsrFwdArgs& a) {
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     }
     const int small_grid = min(b.grid.ntiles, nsm * 4);
-    const int big_grid = min(b.grid.ntiles, nsm * 2);
-    sort_big_kernel<<<big_grid, 1024, big_smem, a.stream>>>(b.header, b.work_order, b.tile_start, b.keys,
-                                                            b.geom, b.records);
-    sort_small_kernel<<<small_grid, 256, small_smem, a.stream>>>(b.header, b.work_order, b.tile_start, b.keys,
-                                                                 b.geom, b.records);
+    const int big_grid = min(b.grid.ntiles, nsm);
+    sort_big_kernel<<<big_grid, 1024, big_smem, a.stream>>>(b.header, b.work_order, b.tile_start, b.keys);
+    sort_small_kernel<<<small_grid, 256, small_smem, a.stream>>>(b.header, b.work_order, b.tile_start, b.keys);
+    gather_records_kernel<<<nsm * 8, 256, 0, a.stream>>>(b.header, b.keys, b.geom, b.records);
     return cudaGetLastError();
 }

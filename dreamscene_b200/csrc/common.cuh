@@ -52,7 +52,7 @@ enum { GSR_H_NUM_PAIRS = 0, GSR_H_MAX_PAIRS = 1, GSR_H_NUM_TILES = 2, GSR_H_OVER
 enum { GSR_C_FWD_QUEUE = 0, GSR_C_BWD_QUEUE = 1, GSR_C_SORT_SMALL = 2, GSR_C_SORT_BIG = 3 };
 
 #define GSR_SORT_SMALL_MAX 4096   // keys sorted by the 256-thread kernel (256 x 16 items)
-#define GSR_SORT_BIG_CHUNK 8192   // keys per smem chunk of the 1024-thread kernel (1024 x 8 items)
+#define GSR_SORT_BIG_CHUNK 16384  // keys per smem chunk of the 1024-thread kernel (1024 x 16 items)
 // Tile counters/cursors are privatised into GSR_COPIES arrays (copy = (gaussian_idx>>5) & mask):
 // same-address L2 atomics serialise at ~30 ns each, so the hottest tile bounds the kernel.
 #define GSR_COPIES 16

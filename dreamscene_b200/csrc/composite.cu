@@ -136,10 +136,12 @@ composite_fwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restric
                     pass = cull_pass(q0.x, q0.y, __float_as_uint(q0.z), X0, Y0);
                 }
                 uint32_t mask = __ballot_sync(0xffffffffu, pass);
+                const float4* sp = reinterpret_cast<const float4*>(&st[sub * 32]);
+                const uint32_t pos0 = (uint32_t)(c * kChunk + sub * 32 + 1);
                 while (mask) {
                     const int b = __ffs(mask) - 1;
                     mask &= mask - 1;
-                    const float4* rp = reinterpret_cast<const float4*>(&st[sub * 32 + b]);
+                    const float4* rp = sp + 3 * b;
                     const float4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
                     const PairEval e = eval_pair(q0.x, q0.y, q0.w, q1.x, q1.y, q1.z, X, Y);
                     float wgt = 0.f;
@@ -154,7 +156,7 @@ composite_fwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restric
                             Cb = fmaf(q2.z, wgt, Cb);
                             Dacc = fmaf(q1.w, wgt, Dacc);
                             T = Tn;
-                            last = (uint32_t)(c * kChunk + sub * 32 + b + 1);
+                            last = pos0 + (uint32_t)b;
                         }
                     }
                     if (SCORE) {
@@ -308,12 +310,14 @@ composite_bwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restric
                     pass = cull_pass(q0.x, q0.y, __float_as_uint(q0.z), X0, Y0);
                 }
                 uint32_t mask = __ballot_sync(0xffffffffu, pass);
+                const float4* sp = reinterpret_cast<const float4*>(&st[sub * 32]);
+                const uint32_t pos0 = (uint32_t)(cbase + sub * 32 + 1);
                 while (mask) {
                     const int b = 31 - __clz(mask);
                     mask &= ~(1u << b);
-                    const float4* rp = reinterpret_cast<const float4*>(&st[sub * 32 + b]);
+                    const float4* rp = sp + 3 * b;
                     const float4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
-                    const uint32_t pos = (uint32_t)(cbase + sub * 32 + b + 1);
+                    const uint32_t pos = pos0 + (uint32_t)b;
                     const PairEval e = eval_pair(q0.x, q0.y, q0.w, q1.x, q1.y, q1.z, X, Y);
                     const bool contrib = e.valid && pos <= last;
                     if (!__any_sync(0xffffffffu, contrib)) continue;

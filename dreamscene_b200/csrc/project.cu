@@ -157,22 +157,49 @@ __device__ __forceinline__ int tile_coord(float v, int gmax) {
 }
 
 // ---- SH ----------------------------------------------------------------------------------
-__device__ __forceinline__ void load_sh(const float* __restrict__ base, int nfloats, bool vec_ok,
-                                        float (&sh)[48]) {
-    if (vec_ok) {
-#pragma unroll
-        for (int q = 0; q < 12; ++q) {
-            if (4 * q < nfloats) {
-                const float4 v = ldg_nc_f4(base + 4 * q);
-                sh[4 * q] = v.x; sh[4 * q + 1] = v.y; sh[4 * q + 2] = v.z; sh[4 * q + 3] = v.w;
+// SH coefficients are staged through shared memory with asynchronous copies (cp.async, no
+// register round trip, all copies of a block in flight at once): a block of kBlock Gaussians owns
+// kBlock rows of `stride` floats.  stride is a multiple of 4 with stride/4 odd, so rows are 16-B
+// aligned and the per-thread LDS.128 row walks are bank-conflict free (8 lanes x 16 B hit 8
+// distinct 4-bank groups).  Only rows of visible Gaussians are fetched.
+constexpr int kBlock = 128;
+
+__host__ __device__ __forceinline__ int sh_row_stride(int M) {
+    int s4 = (3 * M + 3) / 4;
+    if ((s4 & 1) == 0) ++s4;
+    return 4 * s4;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// half a warp per row, two rows per iteration
+__device__ __forceinline__ void stage_sh_rows(const float* __restrict__ shs, int M, int nf, int g0, int P,
+                                              const uint8_t* vis, float* buf, int stride) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int hl = lane & 15, hsel = lane >> 4;
+    const bool vec = ((3 * M) & 3) == 0;
+    const int nchunk = (nf + 3) >> 2;
+    for (int it = 0; it < kBlock / 8; ++it) {
+        const int row = it * 8 + w * 2 + hsel;          // 4 warps x 2 rows per iteration
+        if (g0 + row < P && vis[row]) {
+            const float* src = shs + (size_t)(g0 + row) * 3 * M;
+            float* dst = buf + row * stride;
+            if (vec) {
+                if (hl < nchunk) cp_async16(dst + 4 * hl, src + 4 * hl);
             } else {
-                sh[4 * q] = sh[4 * q + 1] = sh[4 * q + 2] = sh[4 * q + 3] = 0.0f;
+                for (int col = hl; col < nf; col += 16) cp_async4(dst + col, src + col);
             }
         }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 48; ++j) sh[j] = (j < nfloats) ? __ldg(base + j) : 0.0f;
     }
+    cp_async_wait_all();
 }
 
 // basis values for degree <= 3 at unit direction (x,y,z): utils/sh_utils.py:73-102
@@ -199,109 +226,131 @@ __device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, flo
     }
 }
 
-__device__ __forceinline__ void sh_color(const float (&B)[16], const float (&sh)[48], int ncoef,
-                                         float (&raw)[3]) {
+// colour = 0.5 + sum_k B[k]*sh[k][c]; the row is read as float4 chunks (f = 3k + c)
+__device__ __forceinline__ void sh_color(const float (&B)[16], const float* row, int nf, float (&raw)[3]) {
     raw[0] = raw[1] = raw[2] = 0.5f;
+    const float4* r4 = reinterpret_cast<const float4*>(row);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        if (k < ncoef) {
-            raw[0] = fmaf(B[k], sh[3 * k + 0], raw[0]);
-            raw[1] = fmaf(B[k], sh[3 * k + 1], raw[1]);
-            raw[2] = fmaf(B[k], sh[3 * k + 2], raw[2]);
+    for (int q = 0; q < 12; ++q) {
+        if (4 * q < nf) {
+            const float4 v = r4[q];
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int f = 4 * q + e;
+                if (f < nf) raw[f % 3] = fmaf(B[f / 3], vv[e], raw[f % 3]);
+            }
         }
     }
 }
 
 // =========================================================================================
-// Forward: one Gaussian per thread.
+// Forward: one Gaussian per thread, kBlock Gaussians per CTA.
 // =========================================================================================
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kBlock)
 project_sh_kernel(b200gsr_params p, const float* __restrict__ means3D,
                   const float* __restrict__ shs, const float* __restrict__ colors,
                   const float* __restrict__ opac, const float* __restrict__ scales,
                   const float* __restrict__ rots, const float* __restrict__ cov3d,
                   int32_t* __restrict__ radii, uint4* __restrict__ rectdepth,
                   GsrRec* __restrict__ geom, uint32_t* __restrict__ tile_count) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.P) return;
+    extern __shared__ __align__(16) float sh_buf[];
+    __shared__ uint8_t vis_s[kBlock];
+    const int g0 = blockIdx.x * kBlock;
+    const int i = g0 + threadIdx.x;
+    const bool active = i < p.P;
     Cam C;
     load_cam(p, C);
     const GsrTileGrid grid = gsr_grid(p.image_height, p.image_width);
 
-    const float x = __ldg(means3D + 3 * (size_t)i), y = __ldg(means3D + 3 * (size_t)i + 1),
-                z = __ldg(means3D + 3 * (size_t)i + 2);
     Geo g;
-    geo_view(C, x, y, z, g);
+    float x = 0.f, y = 0.f, z = 0.f;
     int radius = 0;
-    uint4 rd = make_uint4(0u, 0u, __float_as_uint(g.tz), 0u);
-    if (g.tz > GSR_NEAR_Z) {
-        geo_rest(C, p, x, y, z, scales, rots, cov3d, i, g);
-        if (g.det != 0.0f) {
-            const float mid = MUL(0.5f, ADD(g.a, g.c));
-            const float sq = SQRT(fmaxf(SUB(MUL(mid, mid), g.det), 0.1f));
-            const float lam = fmaxf(ADD(mid, sq), SUB(mid, sq));
-            float rad_f = ceilf(MUL(3.0f, SQRT(lam)));
-            if (isnan(rad_f)) rad_f = 0.0f;
-            rad_f = fminf(fmaxf(rad_f, 0.0f), 1.0e9f);
-            const int minx = tile_coord(SUB(g.px, rad_f), grid.gx);
-            const int maxx = tile_coord(ADD(ADD(g.px, rad_f), 15.0f), grid.gx);
-            const int miny = tile_coord(SUB(g.py, rad_f), grid.gy);
-            const int maxy = tile_coord(ADD(ADD(g.py, rad_f), 15.0f), grid.gy);
-            const int touched = (maxx - minx) * (maxy - miny);
-            if (touched > 0) {
-                radius = (int)rad_f;
-                rd.x = (uint32_t)minx | ((uint32_t)miny << 16);
-                rd.y = (uint32_t)maxx | ((uint32_t)maxy << 16);
-                rd.w = (uint32_t)touched;
-
-                // colour
-                float rgb[3];
-                if (shs != nullptr) {
-                    float dx = x - C.cam[0], dy = y - C.cam[1], dz = z - C.cam[2];
-                    float dn = sqrtf(dx * dx + dy * dy + dz * dz);
-                    if (dn == 0.0f) dn = 1.0f;
-                    dx /= dn; dy /= dn; dz /= dn;
-                    const int ncoef = (p.sh_degree + 1) * (p.sh_degree + 1);
-                    float sh[48], B[16];
-                    load_sh(shs + (size_t)i * 3 * p.M, 3 * ncoef, (p.M & 3) == 0, sh);
-                    sh_basis(p.sh_degree, dx, dy, dz, B);
-                    sh_color(B, sh, ncoef, rgb);
-                    rgb[0] = fmaxf(rgb[0], 0.0f); rgb[1] = fmaxf(rgb[1], 0.0f); rgb[2] = fmaxf(rgb[2], 0.0f);
-                } else {
-                    rgb[0] = __ldg(colors + 3 * (size_t)i); rgb[1] = __ldg(colors + 3 * (size_t)i + 1);
-                    rgb[2] = __ldg(colors + 3 * (size_t)i + 2);
+    int minx = 0, maxx = 0, miny = 0, maxy = 0;
+    uint4 rd = make_uint4(0u, 0u, 0u, 0u);
+    bool vis = false;
+    if (active) {
+        x = __ldg(means3D + 3 * (size_t)i); y = __ldg(means3D + 3 * (size_t)i + 1);
+        z = __ldg(means3D + 3 * (size_t)i + 2);
+        geo_view(C, x, y, z, g);
+        rd.z = __float_as_uint(g.tz);
+        if (g.tz > GSR_NEAR_Z) {
+            geo_rest(C, p, x, y, z, scales, rots, cov3d, i, g);
+            if (g.det != 0.0f) {
+                const float mid = MUL(0.5f, ADD(g.a, g.c));
+                const float sq = SQRT(fmaxf(SUB(MUL(mid, mid), g.det), 0.1f));
+                const float lam = fmaxf(ADD(mid, sq), SUB(mid, sq));
+                float rad_f = ceilf(MUL(3.0f, SQRT(lam)));
+                if (isnan(rad_f)) rad_f = 0.0f;
+                rad_f = fminf(fmaxf(rad_f, 0.0f), 1.0e9f);
+                minx = tile_coord(SUB(g.px, rad_f), grid.gx);
+                maxx = tile_coord(ADD(ADD(g.px, rad_f), 15.0f), grid.gx);
+                miny = tile_coord(SUB(g.py, rad_f), grid.gy);
+                maxy = tile_coord(ADD(ADD(g.py, rad_f), 15.0f), grid.gy);
+                const int touched = (maxx - minx) * (maxy - miny);
+                if (touched > 0) {
+                    vis = true;
+                    radius = (int)rad_f;
+                    rd.x = (uint32_t)minx | ((uint32_t)miny << 16);
+                    rd.y = (uint32_t)maxx | ((uint32_t)maxy << 16);
+                    rd.w = (uint32_t)touched;
                 }
-                const float o = __ldg(opac + i);
-                // conservative half extents of the region where alpha can reach 1/255
-                float ex = -1.0f, ey = -1.0f;
-                if (o * 255.0f > 1.0f) {
-                    const float tau2 = 2.0f * __logf(o * 255.0f) * 1.01f + 0.01f;
-                    ex = sqrtf(tau2 * g.a) * 1.003f + 0.05f;
-                    ey = sqrtf(tau2 * g.c) * 1.003f + 0.05f;
-                    if (!(ex == ex)) ex = 65504.0f * 2.0f;   // NaN -> never cull
-                    if (!(ey == ey)) ey = 65504.0f * 2.0f;
-                }
-                const __half2 eh = __floats2half2_rn(ex, ey);
-                GsrRec rec;
-                rec.px = g.px; rec.py = g.py;
-                rec.A = -0.5f * GSR_LOG2E * MUL(g.c, g.det_inv);
-                rec.B = GSR_LOG2E * MUL(g.b, g.det_inv);          // -log2e * conic.y, conic.y = -b/det
-                rec.C = -0.5f * GSR_LOG2E * MUL(g.a, g.det_inv);
-                rec.opacity = o; rec.depth = g.tz; rec.idx = (uint32_t)i;
-                rec.r = rgb[0]; rec.g = rgb[1]; rec.b = rgb[2];
-                rec.ext = *reinterpret_cast<const uint32_t*>(&eh);
-                float4* dst = reinterpret_cast<float4*>(geom + i);
-                const float4* src = reinterpret_cast<const float4*>(&rec);
-                dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
-
-                uint32_t* cnt = tile_count + (size_t)((i >> 5) & (GSR_COPIES - 1)) * grid.ntiles;
-                for (int ty = miny; ty < maxy; ++ty)
-                    for (int tx = minx; tx < maxx; ++tx) atomicAdd(cnt + ty * grid.gx + tx, 1u);
             }
         }
+        radii[i] = radius;
+        rectdepth[i] = rd;
     }
-    radii[i] = radius;
-    rectdepth[i] = rd;
+    const int stride = sh_row_stride(p.M);
+    const int ncoef = (p.sh_degree + 1) * (p.sh_degree + 1);
+    if (shs != nullptr) {
+        vis_s[threadIdx.x] = vis;
+        __syncthreads();
+        stage_sh_rows(shs, p.M, 3 * ncoef, g0, p.P, vis_s, sh_buf, stride);
+        __syncthreads();
+    }
+    if (!vis) return;
+
+    // tile counters first: the RED atomics overlap the colour math below
+    uint32_t* cnt = tile_count + (size_t)((i >> 5) & (GSR_COPIES - 1)) * grid.ntiles;
+    for (int ty = miny; ty < maxy; ++ty)
+        for (int tx = minx; tx < maxx; ++tx) atomicAdd(cnt + ty * grid.gx + tx, 1u);
+
+    float rgb[3];
+    if (shs != nullptr) {
+        float dx = x - C.cam[0], dy = y - C.cam[1], dz = z - C.cam[2];
+        float dn = sqrtf(dx * dx + dy * dy + dz * dz);
+        if (dn == 0.0f) dn = 1.0f;
+        dx /= dn; dy /= dn; dz /= dn;
+        float B[16];
+        sh_basis(p.sh_degree, dx, dy, dz, B);
+        sh_color(B, sh_buf + threadIdx.x * stride, 3 * ncoef, rgb);
+        rgb[0] = fmaxf(rgb[0], 0.0f); rgb[1] = fmaxf(rgb[1], 0.0f); rgb[2] = fmaxf(rgb[2], 0.0f);
+    } else {
+        rgb[0] = __ldg(colors + 3 * (size_t)i); rgb[1] = __ldg(colors + 3 * (size_t)i + 1);
+        rgb[2] = __ldg(colors + 3 * (size_t)i + 2);
+    }
+    const float o = __ldg(opac + i);
+    // conservative half extents of the region where alpha can reach 1/255
+    float ex = -1.0f, ey = -1.0f;
+    if (o * 255.0f > 1.0f) {
+        const float tau2 = 2.0f * __logf(o * 255.0f) * 1.01f + 0.01f;
+        ex = sqrtf(tau2 * g.a) * 1.003f + 0.05f;
+        ey = sqrtf(tau2 * g.c) * 1.003f + 0.05f;
+        if (!(ex == ex)) ex = 65504.0f * 2.0f;   // NaN -> never cull
+        if (!(ey == ey)) ey = 65504.0f * 2.0f;
+    }
+    const __half2 eh = __floats2half2_rn(ex, ey);
+    GsrRec rec;
+    rec.px = g.px; rec.py = g.py;
+    rec.A = -0.5f * GSR_LOG2E * MUL(g.c, g.det_inv);
+    rec.B = GSR_LOG2E * MUL(g.b, g.det_inv);          // -log2e * conic.y, conic.y = -b/det
+    rec.C = -0.5f * GSR_LOG2E * MUL(g.a, g.det_inv);
+    rec.opacity = o; rec.depth = g.tz; rec.idx = (uint32_t)i;
+    rec.r = rgb[0]; rec.g = rgb[1]; rec.b = rgb[2];
+    rec.ext = *reinterpret_cast<const uint32_t*>(&eh);
+    float4* dst = reinterpret_cast<float4*>(geom + i);
+    const float4* src = reinterpret_cast<const float4*>(&rec);
+    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
 }
 
 // =========================================================================================
@@ -310,7 +359,7 @@ project_sh_kernel(b200gsr_params p, const float* __restrict__ means3D,
 //   2: sum g*dx*dx  3: sum g*dx*dy  4: sum g*dy*dy
 //   5: sum G*dL/dalpha (dL/dopacity)   6..8: dL/drgb   9: dL/ddepth   10,11: unused
 // =========================================================================================
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kBlock)
 project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
                    const float* __restrict__ shs, const float* __restrict__ colors,
                    const float* __restrict__ scales, const float* __restrict__ rots,
@@ -320,11 +369,22 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
                    float* __restrict__ d_shs, float* __restrict__ d_colors,
                    float* __restrict__ d_opac, float* __restrict__ d_scales,
                    float* __restrict__ d_rots, float* __restrict__ d_cov3d) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.P) return;
-    const bool vis = __ldg(radii + i) > 0;
+    extern __shared__ __align__(16) float sh_buf[];
+    __shared__ uint8_t vis_s[kBlock];
+    const int g0 = blockIdx.x * kBlock;
+    const int i = g0 + threadIdx.x;
+    const bool active = i < p.P;
+    const bool vis = active && (__ldg(radii + i) > 0);
     const int nsh = 3 * p.M;
-    const bool vec_ok = (p.M & 3) == 0;
+    const int stride = sh_row_stride(p.M);
+    const int deg = p.sh_degree;
+    const int ncoef = (deg + 1) * (deg + 1);
+    if (shs != nullptr) {
+        vis_s[threadIdx.x] = vis;
+        __syncthreads();
+        stage_sh_rows(shs, p.M, 3 * ncoef, g0, p.P, vis_s, sh_buf, stride);
+        __syncthreads();
+    }
     float dmean[3] = {0.f, 0.f, 0.f};
     float dm2[2] = {0.f, 0.f};
     float dop = 0.f;
@@ -332,9 +392,6 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
     float drot[4] = {0.f, 0.f, 0.f, 0.f};
     float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float dcol[3] = {0.f, 0.f, 0.f};
-    float dsh[48];
-#pragma unroll
-    for (int j = 0; j < 48; ++j) dsh[j] = 0.f;
 
     if (vis) {
         Cam C;
@@ -444,34 +501,45 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
                              qy * dR[5] + qx * dR[6] + qy * dR[7]);
         }
 
-        // ---- colour -> SH -------------------------------------------------------------------
+        // ---- colour -> SH (coefficients live in this thread's shared-memory row) -------------
         if (shs != nullptr) {
             float vx = x - C.cam[0], vy = y - C.cam[1], vz = z - C.cam[2];
             float dn = sqrtf(vx * vx + vy * vy + vz * vz);
             if (dn == 0.0f) dn = 1.0f;
             const float inv_n = 1.0f / dn;
-            const float ux = vx / dn, uy = vy / dn, uz = vz / dn;
-            const int deg = p.sh_degree;
-            const int ncoef = (deg + 1) * (deg + 1);
-            float sh[48], B[16], raw[3];
-            load_sh(shs + (size_t)i * nsh, 3 * ncoef, vec_ok, sh);
-            sh_basis(deg, ux, uy, uz, B);
-            sh_color(B, sh, ncoef, raw);
+            const float X = vx / dn, Y = vy / dn, Z = vz / dn;
+            float* row = sh_buf + threadIdx.x * stride;
+            const int nf = 3 * ncoef;
+            float B[16], raw[3];
+            sh_basis(deg, X, Y, Z, B);
+            sh_color(B, row, nf, raw);
             float dc3[3];
 #pragma unroll
             for (int c_ = 0; c_ < 3; ++c_) dc3[c_] = (raw[c_] < 0.0f) ? 0.0f : drgb[c_];
+            // s_k = sum_c dL/drgb_c * sh[k][c]; then overwrite the row with dL/dsh (float4 chunks)
+            float s[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k)
-                if (k < ncoef) {
-                    dsh[3 * k] = B[k] * dc3[0]; dsh[3 * k + 1] = B[k] * dc3[1]; dsh[3 * k + 2] = B[k] * dc3[2];
+            for (int k = 0; k < 16; ++k) s[k] = 0.f;
+            float4* r4 = reinterpret_cast<float4*>(row);
+#pragma unroll
+            for (int q = 0; q < 12; ++q) {
+                if (4 * q < nf) {
+                    const float4 v = r4[q];
+                    const float vv[4] = {v.x, v.y, v.z, v.w};
+                    float o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int f = 4 * q + e;
+                        o[e] = 0.f;
+                        if (f < nf) {
+                            s[f / 3] = fmaf(dc3[f % 3], vv[e], s[f / 3]);
+                            o[e] = B[f / 3] * dc3[f % 3];
+                        }
+                    }
+                    r4[q] = make_float4(o[0], o[1], o[2], o[3]);
                 }
+            }
             if (deg > 0) {
-                // s_k = sum_c dL/drgb_c * sh[k][c]
-                float s[16];
-#pragma unroll
-                for (int k = 0; k < 16; ++k)
-                    s[k] = dc3[0] * sh[3 * k] + dc3[1] * sh[3 * k + 1] + dc3[2] * sh[3 * k + 2];
-                const float X = ux, Y = uy, Z = uz;
                 float gx = -SH_C1 * s[3], gy = -SH_C1 * s[1], gz = SH_C1 * s[2];
                 if (deg > 1) {
                     gx += SH_C2_0 * Y * s[4] + SH_C2_2 * (-2.f * X) * s[6] + SH_C2_3 * Z * s[7] + SH_C2_4 * 2.f * X * s[8];
@@ -503,30 +571,44 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
     }
 
     // ---- dense writes (zeros for culled Gaussians) ---------------------------------------
-    d_means3D[3 * (size_t)i] = dmean[0]; d_means3D[3 * (size_t)i + 1] = dmean[1]; d_means3D[3 * (size_t)i + 2] = dmean[2];
-    d_means2D[3 * (size_t)i] = dm2[0]; d_means2D[3 * (size_t)i + 1] = dm2[1]; d_means2D[3 * (size_t)i + 2] = 0.f;
-    d_opac[i] = dop;
-    if (cov3d != nullptr) {
+    if (active) {
+        d_means3D[3 * (size_t)i] = dmean[0]; d_means3D[3 * (size_t)i + 1] = dmean[1]; d_means3D[3 * (size_t)i + 2] = dmean[2];
+        d_means2D[3 * (size_t)i] = dm2[0]; d_means2D[3 * (size_t)i + 1] = dm2[1]; d_means2D[3 * (size_t)i + 2] = 0.f;
+        d_opac[i] = dop;
+        if (cov3d != nullptr) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) d_cov3d[6 * (size_t)i + k] = dcov[k];
-    } else {
-        d_scales[3 * (size_t)i] = dsc[0]; d_scales[3 * (size_t)i + 1] = dsc[1]; d_scales[3 * (size_t)i + 2] = dsc[2];
-        reinterpret_cast<float4*>(d_rots)[i] = make_float4(drot[0], drot[1], drot[2], drot[3]);
+            for (int k = 0; k < 6; ++k) d_cov3d[6 * (size_t)i + k] = dcov[k];
+        } else {
+            d_scales[3 * (size_t)i] = dsc[0]; d_scales[3 * (size_t)i + 1] = dsc[1]; d_scales[3 * (size_t)i + 2] = dsc[2];
+            reinterpret_cast<float4*>(d_rots)[i] = make_float4(drot[0], drot[1], drot[2], drot[3]);
+        }
+        if (shs == nullptr) {
+            d_colors[3 * (size_t)i] = dcol[0]; d_colors[3 * (size_t)i + 1] = dcol[1]; d_colors[3 * (size_t)i + 2] = dcol[2];
+        }
     }
     if (shs != nullptr) {
-        float* dst = d_shs + (size_t)i * nsh;
-        if (vec_ok) {
-#pragma unroll
-            for (int q = 0; q < 12; ++q)
-                if (4 * q < nsh)
-                    stg_na_f4(dst + 4 * q, make_float4(dsh[4 * q], dsh[4 * q + 1], dsh[4 * q + 2], dsh[4 * q + 3]));
-        } else {
-#pragma unroll
-            for (int j = 0; j < 48; ++j)
-                if (j < nsh) dst[j] = dsh[j];
+        // drain the rows with coalesced stores (zeros for culled rows / inactive degrees)
+        __syncthreads();
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        const int hl = lane & 15, hsel = lane >> 4;
+        const int nf = 3 * ncoef, nchunk = (nf + 3) >> 2;
+        const bool vec = (nsh & 3) == 0;
+        for (int it = 0; it < kBlock / 8; ++it) {
+            const int row = it * 8 + w * 2 + hsel;
+            if (g0 + row >= p.P) continue;
+            float* dst = d_shs + (size_t)(g0 + row) * nsh;
+            const bool v = vis_s[row];
+            if (vec) {
+                for (int q = hl; 4 * q < nsh; q += 16) {
+                    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (v && q < nchunk) val = *reinterpret_cast<const float4*>(sh_buf + row * stride + 4 * q);
+                    stg_na_f4(dst + 4 * q, val);
+                }
+            } else {
+                for (int col = hl; col < nsh; col += 16)
+                    dst[col] = (v && col < nf) ? sh_buf[row * stride + col] : 0.0f;
+            }
         }
-    } else {
-        d_colors[3 * (size_t)i] = dcol[0]; d_colors[3 * (size_t)i + 1] = dcol[1]; d_colors[3 * (size_t)i + 2] = dcol[2];
     }
 }
 
@@ -544,7 +626,8 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
 cudaError_t gsr_launch_project(const GsrFwdArgs& a) {
     const int P = a.prm.P;
     if (P == 0) return cudaSuccess;
-    project_sh_kernel<<<(P + 255) / 256, 256, 0, a.stream>>>(
+    const size_t smem = a.shs ? (size_t)kBlock * sh_row_stride(a.prm.M) * sizeof(float) : 0;
+    project_sh_kernel<<<(P + kBlock - 1) / kBlock, kBlock, smem, a.stream>>>(
         a.prm, a.means3D, a.shs, a.colors, a.opac, a.scales, a.rots, a.cov3d, a.radii,
         reinterpret_cast<uint4*>(a.scratch + a.sl.rectdepth),
         reinterpret_cast<GsrRec*>(a.scratch + a.sl.geom),
@@ -555,7 +638,8 @@ cudaError_t gsr_launch_project(const GsrFwdArgs& a) {
 cudaError_t gsr_launch_project_bwd(const GsrBwdArgs& a) {
     const int P = a.prm.P;
     if (P == 0) return cudaSuccess;
-    project_bwd_kernel<<<(P + 255) / 256, 256, 0, a.stream>>>(
+    const size_t smem = a.shs ? (size_t)kBlock * sh_row_stride(a.prm.M) * sizeof(float) : 0;
+    project_bwd_kernel<<<(P + kBlock - 1) / kBlock, kBlock, smem, a.stream>>>(
         a.prm, a.means3D, a.shs, a.colors, a.scales, a.rots, a.cov3d, a.radii,
         reinterpret_cast<const float*>(a.scratch + a.sl.dgeom), a.d_means3D, a.d_means2D, a.d_shs,
         a.d_colors, a.d_opac, a.d_scales, a.d_rots, a.d_cov3d);
