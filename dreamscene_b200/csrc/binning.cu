@@ -129,11 +129,23 @@ scatter_kernel(int P, int gx, int ntiles, uint32_t max_pairs, const uint4* __res
     const int minx = rd.x & 0xffff, miny = rd.x >> 16, maxx = rd.y & 0xffff, maxy = rd.y >> 16;
     const unsigned long long key = ((unsigned long long)rd.z << 32) | (uint32_t)i;
     uint32_t* cur = tile_cursor + (size_t)((i >> 5) & (GSR_COPIES - 1)) * ntiles;
-    for (int ty = miny; ty < maxy; ++ty)
-        for (int tx = minx; tx < maxx; ++tx) {
-            const uint32_t pos = atomicAdd(cur + ty * gx + tx, 1u);
-            if (pos < max_pairs) keys[pos] = key;
+    // The returned atomics are issued in batches of 8 before any dependent store, so up to 8
+    // L2 round trips overlap per thread instead of serialising.
+    const int w = maxx - minx, total = (int)rd.w;
+    for (int base = 0; base < total; base += 8) {
+        uint32_t pos[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int t = base + u;
+            if (t < total) {
+                const int ry = t / w, rx = t - ry * w;
+                pos[u] = atomicAdd(cur + (miny + ry) * gx + (minx + rx), 1u);
+            }
         }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (base + u < total && pos[u] < max_pairs) keys[pos[u]] = key;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
