@@ -159,31 +159,39 @@ scatter_kernel(int P, int gx, int ntiles, uint32_t max_pairs, const uint4* __res
 template <int NT, int ITEMS>
 __device__ __forceinline__ void radix_sort_smem(unsigned long long* s, uint32_t* hist /*[NT/32][256]*/,
                                                 uint32_t* digit_base /*[256]*/, uint32_t* red /*[2]*/,
-                                                int n) {
+                                                int n, bool full64) {
     constexpr int NW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int rows = (n + NW * 32 - 1) / (NW * 32);   // rows per warp actually used (<= ITEMS)
     unsigned long long k[ITEMS];
-    uint32_t vor = 0u, vand = 0xffffffffu;
+    uint32_t vor = 0u, vand = 0xffffffffu, lor = 0u, land = 0xffffffffu;
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         const int e = (w * rows + j) * 32 + lane;
         const bool ok = j < rows && e < n;
         k[j] = ok ? s[e] : ~0ull;
-        if (ok) { vor |= (uint32_t)(k[j] >> 32); vand &= (uint32_t)(k[j] >> 32); }
+        if (ok) {
+            vor |= (uint32_t)(k[j] >> 32); vand &= (uint32_t)(k[j] >> 32);
+            lor |= (uint32_t)k[j]; land &= (uint32_t)k[j];
+        }
     }
     vor = __reduce_or_sync(0xffffffffu, vor);
     vand = __reduce_and_sync(0xffffffffu, vand);
-    if (tid == 0) { red[0] = 0u; red[1] = 0xffffffffu; }
+    lor = __reduce_or_sync(0xffffffffu, lor);
+    land = __reduce_and_sync(0xffffffffu, land);
+    if (tid == 0) { red[0] = 0u; red[1] = 0xffffffffu; red[2] = 0u; red[3] = 0xffffffffu; }
     __syncthreads();
-    if (lane == 0) { atomicOr(&red[0], vor); atomicAnd(&red[1], vand); }
+    if (lane == 0) { atomicOr(&red[0], vor); atomicAnd(&red[1], vand); atomicOr(&red[2], lor); atomicAnd(&red[3], land); }
     __syncthreads();
-    const uint32_t varying = red[0] ^ red[1];   // depth bits that differ somewhere in the list
+    // bits that differ somewhere in the list (depth in the high word, index in the low word)
+    const unsigned long long varying = ((unsigned long long)(red[0] ^ red[1]) << 32) |
+                                       (full64 ? (unsigned long long)(red[2] ^ red[3]) : 0ull);
+    __syncthreads();
 
 #pragma unroll 1
-    for (int shift = 32; shift < 64; shift += 8) {
-        if (((varying >> (shift - 32)) & 0xffu) == 0u) continue;   // constant digit: pass is a no-op
+    for (int shift = full64 ? 0 : 32; shift < 64; shift += 8) {
+        if (((varying >> shift) & 0xffull) == 0ull) continue;   // constant digit: pass is a no-op
         // (1) per-warp histogram (native 32-bit shared-memory atomics)
         for (int d = lane; d < 256; d += 32) hist[w * 256 + d] = 0u;
         __syncwarp();
@@ -243,20 +251,125 @@ __device__ __forceinline__ void radix_sort_smem(unsigned long long* s, uint32_t*
         }
         __syncthreads();
     }
-    // tie pass: runs of equal depth bits are ordered by index (arrival order was arbitrary)
+    if (full64) return;   // the index bytes were sorted too: nothing left to fix
+    // tie pass: runs of equal depth bits are ordered by index (arrival order was arbitrary).
+    // Short runs: the run head insertion-sorts them.  A long run (> 32, e.g. a plane at constant
+    // view depth) would make that quadratic, so the caller re-sorts with the index bytes included.
+    if (tid == 0) red[0] = 0u;
+    __syncthreads();
     for (int i = tid; i < n; i += NT) {
         const uint32_t d = (uint32_t)(s[i] >> 32);
         const bool head = (i == 0 || (uint32_t)(s[i - 1] >> 32) != d) && (i + 1 < n) &&
                           (uint32_t)(s[i + 1] >> 32) == d;
         if (head) {
             int e = i + 1;
-            while (e < n && (uint32_t)(s[e] >> 32) == d) ++e;
+            while (e < n && e - i <= 32 && (uint32_t)(s[e] >> 32) == d) ++e;
+            if (e - i > 32) { red[0] = 1u; continue; }
             for (int a = i + 1; a < e; ++a) {          // insertion sort of s[i, e)
                 const unsigned long long x = s[a];
                 int b = a - 1;
                 while (b >= i && s[b] > x) { s[b + 1] = s[b]; --b; }
                 s[b + 1] = x;
             }
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fast path: one-pass interpolation bucket sort.  Depth bits are mapped monotonically onto NB
+// buckets between the list's min and max; a shared-memory atomic hands every key its slot inside
+// the bucket; then one thread insertion-sorts each (tiny) bucket on the FULL 64-bit key, which
+// also orders equal depths by index.  If any bucket is larger than kBucketLimit (skewed depth
+// distribution) the list falls back to the radix sort above.  Returns with s[0..n) sorted.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBucketLimit = 32;
+
+template <int NT, int ITEMS, int NB>
+__device__ __forceinline__ void tile_sort_smem(unsigned long long* s, uint32_t* hist, uint32_t* digit_base,
+                                               uint32_t* red, int n) {
+    static_assert(NB <= (NT / 32) * 256, "bucket counters alias the radix histogram");
+    static_assert(NB % NT == 0, "whole number of buckets per thread");
+    constexpr int BPT = NB / NT;
+    const int tid = threadIdx.x, lane = tid & 31;
+    uint32_t* cnt = hist;   // NB counters, later exclusive starts
+    unsigned long long k[ITEMS];
+    uint32_t dmin = 0xffffffffu, dmax = 0u;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const int e = j * NT + tid;
+        k[j] = e < n ? s[e] : ~0ull;
+        if (e < n) { dmin = min(dmin, (uint32_t)(k[j] >> 32)); dmax = max(dmax, (uint32_t)(k[j] >> 32)); }
+    }
+    dmin = __reduce_min_sync(0xffffffffu, dmin);
+    dmax = __reduce_max_sync(0xffffffffu, dmax);
+    if (tid == 0) { red[0] = 0xffffffffu; red[1] = 0u; red[2] = 0u; }
+#pragma unroll
+    for (int q = 0; q < BPT; ++q) cnt[q * NT + tid] = 0u;
+    __syncthreads();
+    if (lane == 0) { atomicMin(&red[0], dmin); atomicMax(&red[1], dmax); }
+    __syncthreads();
+    dmin = red[0]; dmax = red[1];
+    const float scale = (float)NB / ((float)(dmax - dmin) + 1.0f);
+    uint32_t rank8[(ITEMS + 3) / 4];   // rank inside the bucket, one byte per item (saturating)
+#pragma unroll
+    for (int j = 0; j < (ITEMS + 3) / 4; ++j) rank8[j] = 0u;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const int e = j * NT + tid;
+        if (e < n) {
+            const uint32_t b = min((uint32_t)(NB - 1), (uint32_t)((float)((uint32_t)(k[j] >> 32) - dmin) * scale));
+            rank8[j >> 2] |= min(atomicAdd(&cnt[b], 1u), 255u) << (8 * (j & 3));
+        }
+    }
+    __syncthreads();
+    // exclusive scan of the NB counters (BPT consecutive counters per thread) + largest bucket
+    uint32_t c[BPT], sum = 0, big = 0;
+#pragma unroll
+    for (int q = 0; q < BPT; ++q) { c[q] = cnt[tid * BPT + q]; sum += c[q]; big = max(big, c[q]); }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    big = __reduce_max_sync(0xffffffffu, big);
+    if (lane == 31) digit_base[tid >> 5] = incl;
+    if (lane == 0 && big > (uint32_t)kBucketLimit) red[2] = 1u;
+    __syncthreads();
+    if (red[2] != 0u) {   // skewed list (uniform branch): robust path; s still holds the input
+        __syncthreads();
+        radix_sort_smem<NT, ITEMS>(s, hist, digit_base, red, n, false);
+        if (red[0] != 0u) {   // long runs of equal depth: sort again on all 64 bits
+            __syncthreads();
+            radix_sort_smem<NT, ITEMS>(s, hist, digit_base, red, n, true);
+        }
+        return;
+    }
+    uint32_t wbase = 0;
+    for (int ww = 0; ww < (tid >> 5); ++ww) wbase += digit_base[ww];
+    uint32_t run = wbase + incl - sum;
+    uint32_t start[BPT];
+#pragma unroll
+    for (int q = 0; q < BPT; ++q) { start[q] = run; cnt[tid * BPT + q] = run; run += c[q]; }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const int e = j * NT + tid;
+        if (e < n) {
+            const uint32_t b = min((uint32_t)(NB - 1), (uint32_t)((float)((uint32_t)(k[j] >> 32) - dmin) * scale));
+            s[cnt[b] + ((rank8[j >> 2] >> (8 * (j & 3))) & 0xffu)] = k[j];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < BPT; ++q) {
+        const int b0 = (int)start[q], m = (int)c[q];
+        for (int a = b0 + 1; a < b0 + m; ++a) {
+            const unsigned long long x = s[a];
+            int b = a - 1;
+            while (b >= b0 && s[b] > x) { s[b + 1] = s[b]; --b; }
+            s[b + 1] = x;
         }
     }
     __syncthreads();
@@ -287,13 +400,13 @@ struct SortSmemSmall {
     unsigned long long keys[GSR_SORT_SMALL_MAX];
     uint32_t hist[8 * 256];
     uint32_t digit_base[256 + 8];
-    uint32_t red[2];
+    uint32_t red[4];
 };
 struct SortSmemBig {
     unsigned long long keys[GSR_SORT_BIG_CHUNK];
     uint32_t hist[32 * 256];
     uint32_t digit_base[256 + 8];
-    uint32_t red[2];
+    uint32_t red[4];
 };
 
 // small tiles: n <= 4096, 256 threads x 16 items
@@ -313,7 +426,7 @@ sort_small_kernel(const uint32_t* __restrict__ header, const uint32_t* __restric
         const int n = (int)(end - beg);
         for (int i = threadIdx.x; i < n; i += 256) sm.keys[i] = keys[beg + i];
         __syncthreads();
-        radix_sort_smem<256, 16>(sm.keys, sm.hist, sm.digit_base, sm.red, n);
+        tile_sort_smem<256, 16, 1024>(sm.keys, sm.hist, sm.digit_base, sm.red, n);
         for (int i = threadIdx.x; i < n; i += 256) keys[beg + i] = sm.keys[i];
         __syncthreads();
     }
@@ -341,7 +454,7 @@ sort_big_kernel(const uint32_t* __restrict__ header, const uint32_t* __restrict_
         if (n <= CH) {
             for (int i = threadIdx.x; i < n; i += 1024) sb[i] = gk[i];
             __syncthreads();
-            radix_sort_smem<1024, 16>(sb, sm.hist, sm.digit_base, sm.red, n);
+            tile_sort_smem<1024, 16, 4096>(sb, sm.hist, sm.digit_base, sm.red, n);
             for (int i = threadIdx.x; i < n; i += 1024) gk[i] = sb[i];
             __syncthreads();
             continue;
@@ -352,7 +465,7 @@ sort_big_kernel(const uint32_t* __restrict__ header, const uint32_t* __restrict_
             const int m = min(CH, n - c0);
             for (int i = threadIdx.x; i < m; i += 1024) sb[i] = __ldcg(gk + c0 + i);
             __syncthreads();
-            radix_sort_smem<1024, 16>(sb, sm.hist, sm.digit_base, sm.red, m);
+            tile_sort_smem<1024, 16, 4096>(sb, sm.hist, sm.digit_base, sm.red, m);
             for (int i = threadIdx.x; i < m; i += 1024) __stcg(gk + c0 + i, sb[i]);
             __syncthreads();
         }

@@ -376,7 +376,7 @@ cudaError_t gsr_launch_composite_fwd(const GsrFwdArgs& a) {
     uint32_t* n_contrib = reinterpret_cast<uint32_t*>(a.saved + a.vl.n_contrib);
     uint32_t* queue = reinterpret_cast<uint32_t*>(a.scratch + a.sl.counters) + GSR_C_FWD_QUEUE;
     const int smem = (int)sizeof(SmemRing);
-    const int nblocks = min(grid.ntiles, g_num_sms() * 4);
+    const int nblocks = min(grid.ntiles, g_num_sms() * 6);
     cudaError_t e;
     if (a.prm.score_flag) {
         e = cudaFuncSetAttribute(composite_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -231,6 +231,26 @@ def test_long_tile_lists_exercise_both_sort_paths_and_overflow_retry():
     check_images(cu, ref)
 
 
+def test_equal_depth_runs_and_skewed_depths_sort_exactly():
+    """100 exact duplicates of each of 80 positions (runs of equal depth bits, ordered by index)
+    plus two tight depth clusters (skewed bucket occupancy -> radix fallback)."""
+    P0, dup, H, W = 80, 100, 64, 64
+    sc, cam, deg = U.make_inputs(P0, H, W, seed=19, radius=0.05, exact_knn=False, scale_mul=40.0)
+    sc = {k: v.repeat_interleave(dup, dim=0).contiguous() for k, v in sc.items()}
+    # second cluster: same duplicates pushed away from the camera along the view axis
+    far = {k: v.clone() for k, v in sc.items()}
+    fwd = -cam.camera_center / cam.camera_center.norm()
+    far["means3D"] = far["means3D"] + fwd * 1.5
+    sc = {k: torch.cat([sc[k], far[k]], dim=0).contiguous() for k in sc}
+    ref = run_oracle(sc, cam, deg)
+    n = ref["ranges"][:, 1] - ref["ranges"][:, 0]
+    assert n.max() > 4096
+    cu = run_cuda(sc, cam, deg)
+    np.testing.assert_array_equal(cu["radii"].cpu().numpy(), ref["radii"].numpy())
+    check_lists(sc, cam, ref)
+    check_images(cu, ref)
+
+
 def test_api_errors_match_reference_messages():
     from dreamscene_b200 import GaussianRasterizer
     sc, cam, deg = U.make_inputs(16, 32, 32)
