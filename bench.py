@@ -42,7 +42,7 @@ WORKLOADS = {
     "cfg1_10k_256": dict(P=10_000, H=256, W=256, radius=0.5, opacity="sigmoid_normal"),
 }
 METRIC = "fwd+bwd Mpix/s @1M Gaussians/1024^2"
-KERNELS_PER_STEP = 9   # project_sh, scan_order, scatter, sort_big, sort_small, gather_records, composite_fwd, composite_bwd, project_bwd
+KERNELS_PER_STEP = 8   # project_sh, scan_order, scatter, sort_big, sort_small, composite_fwd, composite_bwd, project_bwd
 
 
 def measured_peaks():
@@ -209,9 +209,9 @@ def algorithmic_bytes(P, V, D, N, M):
         "project_sh": P * g_in + P * (4 + 16) + V * 48,        # params; radii + rect/depth; geom record
         "scan_order": 0,
         "scatter": P * 16 + D * 8,                               # rect/depth read; key write
-        "tile_sort": D * 8 * 2 + D * 8 + D * 48 + D * 48,        # key read+write (sort); key read, record gather, record write
-        "composite_fwd": D * 48 + N * (12 + 8 + 4),              # records; colour, depth_alpha, n_contrib
-        "composite_bwd": D * 48 + N * (20 + 8) + V * 48,         # records; grads in + T/n_contrib; dgeom
+        "tile_sort": D * 8 * 2,                                  # key read + sorted key write
+        "composite_fwd": D * (8 + 48) + N * (12 + 8 + 4),        # keys + gathered records; colour, depth_alpha, n_contrib
+        "composite_bwd": D * (8 + 48) + N * (20 + 8) + V * 48,   # keys + records; grads in + T/n_contrib; dgeom
         "project_bwd": P * g_in + V * 48 + P * 4 + P * (g_in + 12),  # params, dgeom, radii; grads out
     }
 
@@ -357,7 +357,7 @@ def main():
             "config": {"workload": wl_name, "P": P, "H": H, "W": W, "sh_degree": 3, "M": M,
                        "views_per_step": world, "parallelism": f"view-sharded dp{world}",
                        "visible": V, "tile_pairs": D,
-                       "l2": "inputs larger than L2 (params 236 MB + records %d MB per step)" % (D * 48 // 2**20)},
+                       "l2": "inputs larger than L2 (params 236 MB read + 248 MB grads written + %d MB keys per step)" % (D * 8 // 2**20)},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": mean_ms[dom]},

@@ -25,12 +25,12 @@ class Params(C.Structure):
 
 class SavedLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in ("header", "tile_start", "work_order", "n_contrib",
-                                          "records", "total")]
+                                          "keys", "geom", "total")]
 
 
 class ScratchLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in ("counters", "tile_count", "tile_cursor", "rectdepth",
-                                          "geom", "keys", "dgeom", "total")]
+                                          "dgeom", "total")]
 
 
 _lib = None

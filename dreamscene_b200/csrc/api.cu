@@ -89,7 +89,8 @@ int b200gsr_saved_layout_query(int32_t P, int32_t H, int32_t W, uint64_t max_pai
     out->tile_start = off;  off = align_up(off + ((size_t)g.ntiles + 1) * sizeof(uint32_t));
     out->work_order = off;  off = align_up(off + (size_t)g.ntiles * sizeof(uint32_t));
     out->n_contrib = off;   off = align_up(off + (size_t)H * W * sizeof(uint32_t));
-    out->records = off;     off = align_up(off + (size_t)max_pairs * sizeof(GsrRec));
+    out->keys = off;        off = align_up(off + ((size_t)max_pairs + 2) * sizeof(uint64_t));
+    out->geom = off;        off = align_up(off + (size_t)P * sizeof(GsrRec));
     out->total = off;
     return B200GSR_OK;
 }
@@ -104,8 +105,6 @@ int b200gsr_scratch_layout_query(int32_t P, int32_t H, int32_t W, uint64_t max_p
     out->tile_count = off;  off = align_up(off + (size_t)GSR_COPIES * g.ntiles * sizeof(uint32_t));
     out->tile_cursor = off; off = align_up(off + (size_t)GSR_COPIES * g.ntiles * sizeof(uint32_t));
     out->rectdepth = off;   off = align_up(off + (size_t)P * sizeof(uint4));
-    out->geom = off;        off = align_up(off + (size_t)P * sizeof(GsrRec));
-    out->keys = off;        off = align_up(off + (size_t)max_pairs * sizeof(uint64_t));
     out->dgeom = off;       off = align_up(off + (size_t)P * 12 * sizeof(float));
     out->total = off;
     return B200GSR_OK;

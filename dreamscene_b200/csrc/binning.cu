@@ -14,8 +14,8 @@
 //                       In-smem LSD radix sort (8-bit digits, match.any ranking, constant digit
 //                       bytes skipped) on the depth bits + a tie pass ordering equal depths by
 //                       index; lists longer than one chunk are merged with bitonic merge steps.
-//   gather_records    : expands every sorted entry into its 48-B record -> the tile-major,
-//                       depth-sorted record array the composite kernels stream with TMA.
+//                       The composite kernels gather the 48-B per-Gaussian records on demand
+//                       (cp.async) from the sorted index list, so no record array is materialised.
 #include "common.cuh"
 
 namespace {
@@ -379,23 +379,6 @@ __device__ __forceinline__ int next_pow2(int n) {
     return n <= 1 ? 1 : 1 << (32 - __clz(n - 1));
 }
 
-// Record expansion: sorted[pos] = geom[idx(keys[pos])], one 16-B part per thread (3 per record).
-// Purely memory bound (random 48-B reads that mostly hit L2, streaming writes).
-__global__ void __launch_bounds__(256)
-gather_records_kernel(const uint32_t* __restrict__ header, const unsigned long long* __restrict__ keys,
-                      const GsrRec* __restrict__ geom, GsrRec* __restrict__ records) {
-    const uint32_t n = min(header[GSR_H_NUM_PAIRS], header[GSR_H_MAX_PAIRS]);
-    const float4* g4 = reinterpret_cast<const float4*>(geom);
-    float4* o4 = reinterpret_cast<float4*>(records);
-    const size_t total = 3 * (size_t)n, step = (size_t)gridDim.x * blockDim.x;
-    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += step) {
-        const size_t r = j / 3;
-        const uint32_t part = (uint32_t)(j - 3 * r);
-        const uint32_t idx = (uint32_t)__ldg(keys + r);
-        stg_na_f4(o4 + j, __ldg(g4 + 3 * (size_t)idx + part));
-    }
-}
-
 struct SortSmemSmall {
     unsigned long long keys[GSR_SORT_SMALL_MAX];
     uint32_t hist[8 * 256];
@@ -519,9 +502,7 @@ sort_big_kernel(const uint32_t* __restrict__ header, const uint32_t* __restrict_
 struct BinPtrs {
     GsrTileGrid grid;
     uint32_t *header, *tile_start, *work_order, *tile_count, *tile_cursor;
-    GsrRec* records;
     unsigned long long* keys;
-    const GsrRec* geom;
     const uint4* rectdepth;
 };
 BinPtrs bin_ptrs(const GsrFwdArgs& a) {
@@ -530,11 +511,9 @@ BinPtrs bin_ptrs(const GsrFwdArgs& a) {
     b.header = reinterpret_cast<uint32_t*>(a.saved + a.vl.header);
     b.tile_start = reinterpret_cast<uint32_t*>(a.saved + a.vl.tile_start);
     b.work_order = reinterpret_cast<uint32_t*>(a.saved + a.vl.work_order);
-    b.records = reinterpret_cast<GsrRec*>(a.saved + a.vl.records);
     b.tile_count = reinterpret_cast<uint32_t*>(a.scratch + a.sl.tile_count);
     b.tile_cursor = reinterpret_cast<uint32_t*>(a.scratch + a.sl.tile_cursor);
-    b.keys = reinterpret_cast<unsigned long long*>(a.scratch + a.sl.keys);
-    b.geom = reinterpret_cast<const GsrRec*>(a.scratch + a.sl.geom);
+    b.keys = reinterpret_cast<unsigned long long*>(a.saved + a.vl.keys);
     b.rectdepth = reinterpret_cast<const uint4*>(a.scratch + a.sl.rectdepth);
     return b;
 }
@@ -574,6 +553,5 @@ cudaError_t gsr_launch_sort(const GsrFwdArgs& a) {
     const int big_grid = min(b.grid.ntiles, nsm);
     sort_big_kernel<<<big_grid, 1024, big_smem, a.stream>>>(b.header, b.work_order, b.tile_start, b.keys);
     sort_small_kernel<<<small_grid, 256, small_smem, a.stream>>>(b.header, b.work_order, b.tile_start, b.keys);
-    gather_records_kernel<<<nsm * 8, 256, 0, a.stream>>>(b.header, b.keys, b.geom, b.records);
     return cudaGetLastError();
 }

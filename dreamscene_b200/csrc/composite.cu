@@ -4,8 +4,12 @@
 // in oracle/splat_ref.py::composite).  B200 design:
 //   * persistent CTAs (256 threads = one 16x16 tile, 8 warps x (8x4)-pixel blocks) pull tiles
 //     from a queue ordered longest-list-first;
-//   * a tile's depth-sorted 48-byte records are one contiguous byte range, streamed into a
-//     3-stage shared-memory ring with cp.async.bulk (TMA 1-D, SASS UBLKCP) + mbarrier;
+//   * a tile's list is its contiguous range of the depth-sorted key array; per chunk of 256
+//     entries every thread reads ONE key (coalesced 8-B loads, prefetched two chunks ahead in a
+//     register) and copies that Gaussian's 48-byte record from the L2-resident per-Gaussian array
+//     straight into a double-buffered shared-memory ring with three 16-byte cp.async (LDGSTS):
+//     no register staging, the copies for chunk c+1 fly while chunk c is being blended, and
+//     - because saturated tiles stop early - records past the stopping point are never fetched;
 //   * each warp tests 32 records at a time (one per lane) against its own 8x4 pixel block
 //     (conservative extent test, never changes which pixels blend) and only evaluates the
 //     survivors, in list order, reading them back with broadcast LDS.128;
@@ -14,19 +18,35 @@
 //     butterfly (12 SHFL for 10 values) and committed with ONE coalesced RED instruction.
 #include "common.cuh"
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kChunk = 256;   // records per pipeline stage (12 KB)
-constexpr int kStages = 3;
+constexpr int kChunk = 256;   // list entries per pipeline stage (one per thread)
+// PPL = pixels per lane.  A warp owns an 8 x (4*PPL) pixel block of the 16x16 tile, so a tile
+// needs 8/PPL warps; lane l holds pixels (x0 + l%8, y0 + l/8 + 4*q), q < PPL.
 
 struct __align__(128) SmemRing {
-    GsrRec rec[kStages][kChunk];
-    uint64_t full[kStages];
-    uint32_t work;      // broadcast slot for the tile queue
-    uint32_t maxlast;   // backward: max n_contrib of the tile
+    GsrRec rec[2][kChunk];   // 2 x 12 KB
+    uint32_t work;           // broadcast slot for the tile queue
+    uint32_t maxlast;        // backward: max n_contrib of the tile
 };
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// copy geom[idx(key)] into rec (3 x 16 B)
+__device__ __forceinline__ void gather_record(GsrRec* rec, const GsrRec* __restrict__ geom,
+                                              unsigned long long key) {
+    const char* src = reinterpret_cast<const char*>(geom + (uint32_t)key);
+    char* dst = reinterpret_cast<char*>(rec);
+    cp_async16(dst, src);
+    cp_async16(dst + 16, src + 16);
+    cp_async16(dst + 32, src + 32);
+}
 
 // The blending test, shared verbatim by forward and backward so both take identical decisions.
 struct PairEval {
@@ -46,37 +66,35 @@ __device__ __forceinline__ PairEval eval_pair(float px, float py, float A, float
     return e;
 }
 
+template <int PPL>
 __device__ __forceinline__ bool cull_pass(float px, float py, uint32_t ext, float X0, float Y0) {
-    // block covers pixel centres [X0, X0+7] x [Y0, Y0+3]
+    // block covers pixel centres [X0, X0+7] x [Y0, Y0+4*PPL-1]
     const __half2 eh = *reinterpret_cast<const __half2*>(&ext);
     const float2 e = __half22float2(eh);
     const float ddx = fmaxf(fmaxf(X0 - px, px - (X0 + 7.0f)), 0.0f);
-    const float ddy = fmaxf(fmaxf(Y0 - py, py - (Y0 + 3.0f)), 0.0f);
+    const float ddy = fmaxf(fmaxf(Y0 - py, py - (Y0 + (float)(4 * PPL - 1))), 0.0f);
     return (ddx <= e.x) && (ddy <= e.y);
 }
 
 // =============================================================================================
 // Forward
 // =============================================================================================
-template <bool SCORE>
-__global__ void __launch_bounds__(kThreads)
+template <bool SCORE, int PPL>
+__global__ void __launch_bounds__(256 / PPL)
 composite_fwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restrict__ header,
                      const uint32_t* __restrict__ work_order,
-                     const uint32_t* __restrict__ tile_start, const GsrRec* __restrict__ records,
+                     const uint32_t* __restrict__ tile_start,
+                     const unsigned long long* __restrict__ keys, const GsrRec* __restrict__ geom,
                      const float* __restrict__ bg, uint32_t* __restrict__ queue,
                      float* __restrict__ out_color, float* __restrict__ out_depth_alpha,
                      uint32_t* __restrict__ n_contrib, float* __restrict__ score) {
+    constexpr int kThreads = 256 / PPL;
+    constexpr int kPer = kChunk / kThreads;   // list entries gathered per thread per chunk
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SmemRing& sm = *reinterpret_cast<SmemRing*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&sm.full[s], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
     const uint32_t max_pairs = header[GSR_H_MAX_PAIRS];
     const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
-    uint32_t gc = 0;   // chunks issued so far by this CTA (slot = gc % kStages, parity = (gc/kStages)&1)
 
     for (;;) {
         if (tid == 0) sm.work = atomicAdd(queue, 1u);
@@ -90,50 +108,59 @@ composite_fwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restric
         if (beg > end) beg = end;
         const int n = (int)(end - beg);
         const int nchunks = (n + kChunk - 1) / kChunk;
+        const unsigned long long* tk = keys + beg;
         const int tyi = tile / gx, txi = tile - tyi * gx;
-        const int X0i = txi * GSR_TILE + (wid & 1) * 8, Y0i = tyi * GSR_TILE + (wid >> 1) * 4;
+        const int X0i = txi * GSR_TILE + (wid & 1) * 8, Y0i = tyi * GSR_TILE + (wid >> 1) * (4 * PPL);
         const int Xi = X0i + (lane & 7), Yi = Y0i + (lane >> 3);
-        const float X0 = (float)X0i, Y0 = (float)Y0i, X = (float)Xi, Y = (float)Yi;
-        const bool inside = Xi < W && Yi < H;
-        bool done = !inside;
-        float T = 1.0f, Cr = 0.f, Cg = 0.f, Cb = 0.f, Dacc = 0.f;
-        uint32_t last = 0;
-
-        // prologue: prefetch up to kStages-1 chunks
-        if (tid == 0) {
-            const int npre = min(nchunks, kStages - 1);
-            for (int c = 0; c < npre; ++c) {
-                const uint32_t slot = (gc + c) % kStages;
-                const uint32_t cnt = (uint32_t)min(kChunk, n - c * kChunk);
-                mbar_expect_tx(&sm.full[slot], cnt * (uint32_t)sizeof(GsrRec));
-                bulk_g2s(sm.rec[slot], records + beg + (size_t)c * kChunk, cnt * (uint32_t)sizeof(GsrRec),
-                         &sm.full[slot]);
-            }
+        const float X0 = (float)X0i, Y0 = (float)Y0i, X = (float)Xi;
+        bool inside[PPL], done[PPL];
+        float Y[PPL], T[PPL], Cr[PPL], Cg[PPL], Cb[PPL], Dacc[PPL];
+        uint32_t last[PPL];
+        bool all_done = true;
+#pragma unroll
+        for (int q = 0; q < PPL; ++q) {
+            inside[q] = Xi < W && (Yi + 4 * q) < H;
+            done[q] = !inside[q];
+            all_done = all_done && done[q];
+            Y[q] = (float)(Yi + 4 * q);
+            T[q] = 1.0f; Cr[q] = Cg[q] = Cb[q] = Dacc[q] = 0.f; last[q] = 0;
         }
-        int c = 0;
-        for (; c < nchunks; ++c) {
-            // everyone has finished chunk c-1 -> its slot may be refilled; also the CTA early-out
-            const int ndone = __syncthreads_count(done);
+
+        // prologue: gather chunk 0, prefetch the keys of chunk 1
+        unsigned long long knext[kPer];
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const int e = u * kThreads + tid;
+            if (e < n) gather_record(&sm.rec[0][e], geom, __ldg(tk + e));
+            knext[u] = (kChunk + e < n) ? __ldg(tk + kChunk + e) : 0ull;
+        }
+        cp_async_commit();
+
+        for (int c = 0; c < nchunks; ++c) {
+            cp_async_wait_all();   // my copies for chunk c have landed
+            // barrier: everyone's copies for chunk c are visible, everyone is done with chunk c-1;
+            // it doubles as the CTA-wide early-out vote
+            const int ndone = __syncthreads_count(all_done);
             if (ndone == kThreads) break;
-            if (tid == 0 && c + kStages - 1 < nchunks) {
-                const int cn = c + kStages - 1;
-                const uint32_t slot = (gc + cn) % kStages;
-                const uint32_t cnt = (uint32_t)min(kChunk, n - cn * kChunk);
-                mbar_expect_tx(&sm.full[slot], cnt * (uint32_t)sizeof(GsrRec));
-                bulk_g2s(sm.rec[slot], records + beg + (size_t)cn * kChunk, cnt * (uint32_t)sizeof(GsrRec),
-                         &sm.full[slot]);
+            // issue the gathers for chunk c+1 (they fly while chunk c is blended), then fetch the
+            // keys of chunk c+2
+#pragma unroll
+            for (int u = 0; u < kPer; ++u) {
+                const int e = u * kThreads + tid;
+                if ((c + 1) * kChunk + e < n) gather_record(&sm.rec[(c + 1) & 1][e], geom, knext[u]);
+                knext[u] = ((c + 2) * kChunk + e < n) ? __ldg(tk + (c + 2) * kChunk + e) : 0ull;
             }
-            const uint32_t g = gc + c, slot = g % kStages;
-            mbar_wait(&sm.full[slot], (g / kStages) & 1u);
-            const GsrRec* st = sm.rec[slot];
+            cp_async_commit();
+
+            const GsrRec* st = sm.rec[c & 1];
             const int cnt = min(kChunk, n - c * kChunk);
-            if (__all_sync(0xffffffffu, done)) continue;   // this warp is saturated
+            if (__all_sync(0xffffffffu, all_done)) continue;   // this warp is saturated
             for (int sub = 0; sub * 32 < cnt; ++sub) {
                 const int r = sub * 32 + lane;
                 bool pass = false;
                 if (r < cnt) {
                     const float4 q0 = *reinterpret_cast<const float4*>(&st[r]);
-                    pass = cull_pass(q0.x, q0.y, __float_as_uint(q0.z), X0, Y0);
+                    pass = cull_pass<PPL>(q0.x, q0.y, __float_as_uint(q0.z), X0, Y0);
                 }
                 uint32_t mask = __ballot_sync(0xffffffffu, pass);
                 const float4* sp = reinterpret_cast<const float4*>(&st[sub * 32]);
@@ -143,49 +170,52 @@ composite_fwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restric
                     mask &= mask - 1;
                     const float4* rp = sp + 3 * b;
                     const float4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
-                    const PairEval e = eval_pair(q0.x, q0.y, q0.w, q1.x, q1.y, q1.z, X, Y);
-                    float wgt = 0.f;
-                    if (e.valid && !done) {
-                        const float Tn = T * (1.0f - e.alpha);
-                        if (Tn < GSR_T_STOP) {
-                            done = true;
-                        } else {
-                            wgt = e.alpha * T;
-                            Cr = fmaf(q2.x, wgt, Cr);
-                            Cg = fmaf(q2.y, wgt, Cg);
-                            Cb = fmaf(q2.z, wgt, Cb);
-                            Dacc = fmaf(q1.w, wgt, Dacc);
-                            T = Tn;
-                            last = pos0 + (uint32_t)b;
+                    float wsum = 0.f;
+#pragma unroll
+                    for (int q = 0; q < PPL; ++q) {
+                        const PairEval e = eval_pair(q0.x, q0.y, q0.w, q1.x, q1.y, q1.z, X, Y[q]);
+                        if (e.valid && !done[q]) {
+                            const float Tn = T[q] * (1.0f - e.alpha);
+                            if (Tn < GSR_T_STOP) {
+                                done[q] = true;
+                            } else {
+                                const float wgt = e.alpha * T[q];
+                                Cr[q] = fmaf(q2.x, wgt, Cr[q]);
+                                Cg[q] = fmaf(q2.y, wgt, Cg[q]);
+                                Cb[q] = fmaf(q2.z, wgt, Cb[q]);
+                                Dacc[q] = fmaf(q1.w, wgt, Dacc[q]);
+                                T[q] = Tn;
+                                last[q] = pos0 + (uint32_t)b;
+                                if (SCORE) wsum += wgt;
+                            }
                         }
                     }
                     if (SCORE) {
-                        float s = wgt;
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                        if (lane == 0 && s != 0.f) atomicAdd(score + __float_as_uint(q2.w), s);
+                        for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+                        if (lane == 0 && wsum != 0.f) atomicAdd(score + __float_as_uint(q2.w), wsum);
                     }
                 }
-                if (__all_sync(0xffffffffu, done)) break;
+                all_done = true;
+#pragma unroll
+                for (int q = 0; q < PPL; ++q) all_done = all_done && done[q];
+                if (__all_sync(0xffffffffu, all_done)) break;
             }
         }
-        // drain chunks that were prefetched but never consumed, keep the ring position in step
-        const int issued = min(nchunks, c + kStages - 1);
-        if (tid == 0)
-            for (int k = c; k < issued; ++k) {
-                const uint32_t g = gc + k;
-                mbar_wait(&sm.full[g % kStages], (g / kStages) & 1u);
-            }
-        gc += (uint32_t)issued;
+        cp_async_wait_all();   // never leave copies in flight across tiles (early-out case)
 
-        if (inside) {
-            const size_t pix = (size_t)Yi * W + Xi, plane = (size_t)H * W;
-            out_color[pix] = fmaf(T, bg0, Cr);
-            out_color[plane + pix] = fmaf(T, bg1, Cg);
-            out_color[2 * plane + pix] = fmaf(T, bg2, Cb);
-            out_depth_alpha[pix] = Dacc;
-            out_depth_alpha[plane + pix] = T;
-            n_contrib[pix] = last;
+        const size_t plane = (size_t)H * W;
+#pragma unroll
+        for (int q = 0; q < PPL; ++q) {
+            if (inside[q]) {
+                const size_t pix = (size_t)(Yi + 4 * q) * W + Xi;
+                out_color[pix] = fmaf(T[q], bg0, Cr[q]);
+                out_color[plane + pix] = fmaf(T[q], bg1, Cg[q]);
+                out_color[2 * plane + pix] = fmaf(T[q], bg2, Cb[q]);
+                out_depth_alpha[pix] = Dacc[q];
+                out_depth_alpha[plane + pix] = T[q];
+                n_contrib[pix] = last[q];
+            }
         }
     }
 }
@@ -217,28 +247,26 @@ __device__ __forceinline__ int bwd_value_index(int lane) {
     return n >= 1 ? base : -1;
 }
 
-__global__ void __launch_bounds__(kThreads)
+template <int PPL>
+__global__ void __launch_bounds__(256 / PPL)
 composite_bwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restrict__ header,
                      const uint32_t* __restrict__ work_order,
-                     const uint32_t* __restrict__ tile_start, const GsrRec* __restrict__ records,
+                     const uint32_t* __restrict__ tile_start,
+                     const unsigned long long* __restrict__ keys, const GsrRec* __restrict__ geom,
                      const float* __restrict__ bg, uint32_t* __restrict__ queue,
                      const float* __restrict__ out_depth_alpha,
                      const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dcolor,
                      const float* __restrict__ dL_ddepth_alpha, float* __restrict__ dgeom) {
+    constexpr int kThreads = 256 / PPL;
+    constexpr int kPer = kChunk / kThreads;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SmemRing& sm = *reinterpret_cast<SmemRing*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&sm.full[s], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
     const uint32_t max_pairs = header[GSR_H_MAX_PAIRS];
     const uint32_t nonempty = header[GSR_H_NUM_NONEMPTY];
     const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
     const int vidx = bwd_value_index(lane);
     const bool commit_lane = (vidx >= 0) && !(lane & 1);
-    uint32_t gc = 0;
 
     for (;;) {
         if (tid == 0) { sm.work = atomicAdd(queue, 1u); sm.maxlast = 0; }
@@ -249,55 +277,64 @@ composite_bwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restric
         uint32_t beg = tile_start[tile], end = tile_start[tile + 1];
         if (end > max_pairs) end = max_pairs;
         if (beg > end) beg = end;
+        const unsigned long long* tk = keys + beg;
         const int tyi = tile / gx, txi = tile - tyi * gx;
-        const int X0i = txi * GSR_TILE + (wid & 1) * 8, Y0i = tyi * GSR_TILE + (wid >> 1) * 4;
+        const int X0i = txi * GSR_TILE + (wid & 1) * 8, Y0i = tyi * GSR_TILE + (wid >> 1) * (4 * PPL);
         const int Xi = X0i + (lane & 7), Yi = Y0i + (lane >> 3);
-        const float X0 = (float)X0i, Y0 = (float)Y0i, X = (float)Xi, Y = (float)Yi;
-        const bool inside = Xi < W && Yi < H;
-        const size_t pix = (size_t)Yi * W + Xi, plane = (size_t)H * W;
-        uint32_t last = 0;
-        float Tfinal = 1.f, dC0 = 0.f, dC1 = 0.f, dC2 = 0.f, dD = 0.f, dT = 0.f;
-        if (inside) {
-            last = n_contrib[pix];
-            Tfinal = out_depth_alpha[plane + pix];
-            dC0 = dL_dcolor[pix]; dC1 = dL_dcolor[plane + pix]; dC2 = dL_dcolor[2 * plane + pix];
-            dD = dL_ddepth_alpha[pix]; dT = dL_ddepth_alpha[plane + pix];
+        const float X0 = (float)X0i, Y0 = (float)Y0i, X = (float)Xi;
+        const size_t plane = (size_t)H * W;
+        uint32_t last[PPL];
+        float Y[PPL], Tfinal[PPL], dC0[PPL], dC1[PPL], dC2[PPL], dD[PPL], bgterm[PPL];
+        float T[PPL], accR[PPL], accG[PPL], accB[PPL], accD[PPL];
+        uint32_t lmax = 0;
+#pragma unroll
+        for (int q = 0; q < PPL; ++q) {
+            const int yq = Yi + 4 * q;
+            Y[q] = (float)yq;
+            last[q] = 0; Tfinal[q] = 1.f; dC0[q] = dC1[q] = dC2[q] = dD[q] = 0.f;
+            float dT = 0.f;
+            if (Xi < W && yq < H) {
+                const size_t pix = (size_t)yq * W + Xi;
+                last[q] = n_contrib[pix];
+                Tfinal[q] = out_depth_alpha[plane + pix];
+                dC0[q] = dL_dcolor[pix]; dC1[q] = dL_dcolor[plane + pix]; dC2[q] = dL_dcolor[2 * plane + pix];
+                dD[q] = dL_ddepth_alpha[pix]; dT = dL_ddepth_alpha[plane + pix];
+            }
+            if ((int)last[q] > (int)(end - beg)) last[q] = end - beg;   // overflow safety
+            bgterm[q] = bg0 * dC0[q] + bg1 * dC1[q] + bg2 * dC2[q] + dT;
+            T[q] = Tfinal[q]; accR[q] = accG[q] = accB[q] = accD[q] = 0.f;
+            lmax = max(lmax, last[q]);
         }
-        if ((int)last > (int)(end - beg)) last = end - beg;   // overflow safety
-        const uint32_t wmax = __reduce_max_sync(0xffffffffu, last);
+        const uint32_t wmax = __reduce_max_sync(0xffffffffu, lmax);
         if (lane == 0 && wmax) atomicMax(&sm.maxlast, wmax);
         __syncthreads();
         const int n = (int)sm.maxlast;        // only entries [0, n) were ever blended
         __syncthreads();   // maxlast/work read by all before thread 0 resets them
         const int nchunks = (n + kChunk - 1) / kChunk;
-        const float bgterm = bg0 * dC0 + bg1 * dC1 + bg2 * dC2 + dT;
-        float T = Tfinal, accR = 0.f, accG = 0.f, accB = 0.f, accD = 0.f;
 
         // chunks are visited from the back: visit k <-> chunk index nchunks-1-k
-        if (tid == 0) {
-            const int npre = min(nchunks, kStages - 1);
-            for (int k = 0; k < npre; ++k) {
-                const int cidx = nchunks - 1 - k;
-                const uint32_t slot = (gc + k) % kStages;
-                const uint32_t cnt = (uint32_t)min(kChunk, n - cidx * kChunk);
-                mbar_expect_tx(&sm.full[slot], cnt * (uint32_t)sizeof(GsrRec));
-                bulk_g2s(sm.rec[slot], records + beg + (size_t)cidx * kChunk, cnt * (uint32_t)sizeof(GsrRec),
-                         &sm.full[slot]);
-            }
+        unsigned long long knext[kPer];
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const int e = u * kThreads + tid;
+            const int c0 = (nchunks - 1) * kChunk + e, c1 = (nchunks - 2) * kChunk + e;
+            if (nchunks > 0 && c0 < n) gather_record(&sm.rec[0][e], geom, __ldg(tk + c0));
+            knext[u] = (nchunks > 1) ? __ldg(tk + c1) : 0ull;   // earlier chunks are always full
         }
+        cp_async_commit();
+
         for (int k = 0; k < nchunks; ++k) {
-            __syncthreads();   // visit k-1 fully consumed -> its slot may be refilled
-            if (tid == 0 && k + kStages - 1 < nchunks) {
-                const int kn = k + kStages - 1, cidx = nchunks - 1 - kn;
-                const uint32_t slot = (gc + kn) % kStages;
-                const uint32_t cnt = (uint32_t)min(kChunk, n - cidx * kChunk);
-                mbar_expect_tx(&sm.full[slot], cnt * (uint32_t)sizeof(GsrRec));
-                bulk_g2s(sm.rec[slot], records + beg + (size_t)cidx * kChunk, cnt * (uint32_t)sizeof(GsrRec),
-                         &sm.full[slot]);
+            cp_async_wait_all();
+            __syncthreads();   // chunk of visit k visible to all, visit k-1 fully consumed
+#pragma unroll
+            for (int u = 0; u < kPer; ++u) {
+                const int e = u * kThreads + tid;
+                if (k + 1 < nchunks) gather_record(&sm.rec[(k + 1) & 1][e], geom, knext[u]);
+                knext[u] = (k + 2 < nchunks) ? __ldg(tk + (nchunks - 3 - k) * kChunk + e) : 0ull;
             }
-            const uint32_t g = gc + k, slot = g % kStages;
-            mbar_wait(&sm.full[slot], (g / kStages) & 1u);
-            const GsrRec* st = sm.rec[slot];
+            cp_async_commit();
+
+            const GsrRec* st = sm.rec[k & 1];
             const int cidx = nchunks - 1 - k;
             const int cnt = min(kChunk, n - cidx * kChunk);
             const int cbase = cidx * kChunk;
@@ -307,7 +344,7 @@ composite_bwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restric
                 bool pass = false;
                 if (r < cnt && (uint32_t)(cbase + r) < wmax) {
                     const float4 q0 = *reinterpret_cast<const float4*>(&st[r]);
-                    pass = cull_pass(q0.x, q0.y, __float_as_uint(q0.z), X0, Y0);
+                    pass = cull_pass<PPL>(q0.x, q0.y, __float_as_uint(q0.z), X0, Y0);
                 }
                 uint32_t mask = __ballot_sync(0xffffffffu, pass);
                 const float4* sp = reinterpret_cast<const float4*>(&st[sub * 32]);
@@ -318,31 +355,43 @@ composite_bwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restric
                     const float4* rp = sp + 3 * b;
                     const float4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
                     const uint32_t pos = pos0 + (uint32_t)b;
-                    const PairEval e = eval_pair(q0.x, q0.y, q0.w, q1.x, q1.y, q1.z, X, Y);
-                    const bool contrib = e.valid && pos <= last;
-                    if (!__any_sync(0xffffffffu, contrib)) continue;
+                    PairEval e[PPL];
+                    bool contrib[PPL], any = false;
+#pragma unroll
+                    for (int q = 0; q < PPL; ++q) {
+                        e[q] = eval_pair(q0.x, q0.y, q0.w, q1.x, q1.y, q1.z, X, Y[q]);
+                        contrib[q] = e[q].valid && pos <= last[q];
+                        any = any || contrib[q];
+                    }
+                    if (!__any_sync(0xffffffffu, any)) continue;
                     float v[10];
 #pragma unroll
                     for (int j = 0; j < 10; ++j) v[j] = 0.f;
-                    if (contrib) {
-                        const float om = 1.0f - e.alpha;
-                        const float rom = rcp_approx(om);
-                        T = T * rom;                       // transmittance in front of this entry
-                        const float wgt = e.alpha * T;
-                        float dLda = (q2.x - accR) * dC0 + (q2.y - accG) * dC1 + (q2.z - accB) * dC2 +
-                                     (q1.w - accD) * dD;
-                        dLda = dLda * T - (Tfinal * rom) * bgterm;
-                        accR = fmaf(e.alpha, q2.x - accR, accR);
-                        accG = fmaf(e.alpha, q2.y - accG, accG);
-                        accB = fmaf(e.alpha, q2.z - accB, accB);
-                        accD = fmaf(e.alpha, q1.w - accD, accD);
-                        const float gG = q1.z * dLda * e.G;   // dL/dG * G (no zeroing under the 0.99 clamp)
-                        const float gxs = 2.0f * q0.w * e.dx + q1.x * e.dy;
-                        const float gys = 2.0f * q1.y * e.dy + q1.x * e.dx;
-                        v[0] = gG * gxs; v[1] = gG * gys;
-                        v[2] = gG * e.dx * e.dx; v[3] = gG * e.dx * e.dy; v[4] = gG * e.dy * e.dy;
-                        v[5] = e.G * dLda;
-                        v[6] = wgt * dC0; v[7] = wgt * dC1; v[8] = wgt * dC2; v[9] = wgt * dD;
+#pragma unroll
+                    for (int q = 0; q < PPL; ++q) {
+                        if (contrib[q]) {
+                            const float alpha = e[q].alpha, dx = e[q].dx, dy = e[q].dy;
+                            const float om = 1.0f - alpha;
+                            const float rom = rcp_approx(om);
+                            T[q] = T[q] * rom;                    // transmittance in front of this entry
+                            const float wgt = alpha * T[q];
+                            float dLda = (q2.x - accR[q]) * dC0[q] + (q2.y - accG[q]) * dC1[q] +
+                                         (q2.z - accB[q]) * dC2[q] + (q1.w - accD[q]) * dD[q];
+                            dLda = dLda * T[q] - (Tfinal[q] * rom) * bgterm[q];
+                            accR[q] = fmaf(alpha, q2.x - accR[q], accR[q]);
+                            accG[q] = fmaf(alpha, q2.y - accG[q], accG[q]);
+                            accB[q] = fmaf(alpha, q2.z - accB[q], accB[q]);
+                            accD[q] = fmaf(alpha, q1.w - accD[q], accD[q]);
+                            const float gG = q1.z * dLda * e[q].G;   // dL/dG * G (no zeroing under the 0.99 clamp)
+                            const float gxs = 2.0f * q0.w * dx + q1.x * dy;
+                            const float gys = 2.0f * q1.y * dy + q1.x * dx;
+                            v[0] = fmaf(gG, gxs, v[0]); v[1] = fmaf(gG, gys, v[1]);
+                            v[2] = fmaf(gG * dx, dx, v[2]); v[3] = fmaf(gG * dx, dy, v[3]);
+                            v[4] = fmaf(gG * dy, dy, v[4]);
+                            v[5] = fmaf(e[q].G, dLda, v[5]);
+                            v[6] = fmaf(wgt, dC0[q], v[6]); v[7] = fmaf(wgt, dC1[q], v[7]);
+                            v[8] = fmaf(wgt, dC2[q], v[8]); v[9] = fmaf(wgt, dD[q], v[9]);
+                        }
                     }
                     halve<10, 16>(v, lane & 16);
                     halve<5, 8>(v, lane & 8);
@@ -353,7 +402,7 @@ composite_bwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restric
                 }
             }
         }
-        gc += (uint32_t)nchunks;
+        cp_async_wait_all();
     }
 }
 
@@ -366,50 +415,74 @@ static int g_num_sms() {
     return nsm;
 }
 
-cudaError_t gsr_launch_composite_fwd(const GsrFwdArgs& a) {
-    const GsrTileGrid grid = gsr_grid(a.prm.image_height, a.prm.image_width);
-    if (grid.ntiles == 0) return cudaSuccess;
-    const uint32_t* header = reinterpret_cast<const uint32_t*>(a.saved + a.vl.header);
-    const uint32_t* tile_start = reinterpret_cast<const uint32_t*>(a.saved + a.vl.tile_start);
-    const uint32_t* work_order = reinterpret_cast<const uint32_t*>(a.saved + a.vl.work_order);
-    const GsrRec* records = reinterpret_cast<const GsrRec*>(a.saved + a.vl.records);
-    uint32_t* n_contrib = reinterpret_cast<uint32_t*>(a.saved + a.vl.n_contrib);
-    uint32_t* queue = reinterpret_cast<uint32_t*>(a.scratch + a.sl.counters) + GSR_C_FWD_QUEUE;
+static int g_ppl() {
+    // pixels per lane of the composite kernels; 1 is the tuned default (finer culling, more warps
+    // per tile; measured 1.05 vs 1.14 ms/step at 1M/1024^2).  B200GSR_PPL=2 for A/B runs.
+    static int ppl = [] {
+        const char* e = getenv("B200GSR_PPL");
+        return (e && e[0] == '2') ? 2 : 1;
+    }();
+    return ppl;
+}
+
+struct CompPtrs {
+    GsrTileGrid grid;
+    const uint32_t *header, *tile_start, *work_order;
+    const unsigned long long* keys;
+    const GsrRec* geom;
+    uint32_t* n_contrib;
+};
+static CompPtrs comp_ptrs(const uint8_t* saved, const b200gsr_saved_layout& vl, int H, int W) {
+    CompPtrs c;
+    c.grid = gsr_grid(H, W);
+    c.header = reinterpret_cast<const uint32_t*>(saved + vl.header);
+    c.tile_start = reinterpret_cast<const uint32_t*>(saved + vl.tile_start);
+    c.work_order = reinterpret_cast<const uint32_t*>(saved + vl.work_order);
+    c.keys = reinterpret_cast<const unsigned long long*>(saved + vl.keys);
+    c.geom = reinterpret_cast<const GsrRec*>(saved + vl.geom);
+    c.n_contrib = reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(saved) + vl.n_contrib);
+    return c;
+}
+
+template <bool SCORE, int PPL>
+static cudaError_t launch_fwd(const GsrFwdArgs& a, int nblocks, const CompPtrs& c, uint32_t* queue) {
     const int smem = (int)sizeof(SmemRing);
-    const int nblocks = min(grid.ntiles, g_num_sms() * 6);
-    cudaError_t e;
-    if (a.prm.score_flag) {
-        e = cudaFuncSetAttribute(composite_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        composite_fwd_kernel<true><<<nblocks, kThreads, smem, a.stream>>>(
-            a.prm.image_height, a.prm.image_width, grid.gx, grid.ntiles, header, work_order, tile_start,
-            records, a.prm.bg, queue, a.out_color, a.out_depth_alpha, n_contrib, a.score);
-    } else {
-        e = cudaFuncSetAttribute(composite_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        composite_fwd_kernel<false><<<nblocks, kThreads, smem, a.stream>>>(
-            a.prm.image_height, a.prm.image_width, grid.gx, grid.ntiles, header, work_order, tile_start,
-            records, a.prm.bg, queue, a.out_color, a.out_depth_alpha, n_contrib, a.score);
-    }
+    cudaError_t e = cudaFuncSetAttribute(composite_fwd_kernel<SCORE, PPL>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    composite_fwd_kernel<SCORE, PPL><<<nblocks, 256 / PPL, smem, a.stream>>>(
+        a.prm.image_height, a.prm.image_width, c.grid.gx, c.grid.ntiles, c.header, c.work_order, c.tile_start,
+        c.keys, c.geom, a.prm.bg, queue, a.out_color, a.out_depth_alpha, c.n_contrib, a.score);
+    return cudaGetLastError();
+}
+
+cudaError_t gsr_launch_composite_fwd(const GsrFwdArgs& a) {
+    const CompPtrs c = comp_ptrs(a.saved, a.vl, a.prm.image_height, a.prm.image_width);
+    if (c.grid.ntiles == 0) return cudaSuccess;
+    uint32_t* queue = reinterpret_cast<uint32_t*>(a.scratch + a.sl.counters) + GSR_C_FWD_QUEUE;
+    const int ppl = g_ppl();
+    const int nblocks = min(c.grid.ntiles, g_num_sms() * 6);
+    if (a.prm.score_flag)
+        return ppl == 2 ? launch_fwd<true, 2>(a, nblocks, c, queue) : launch_fwd<true, 1>(a, nblocks, c, queue);
+    return ppl == 2 ? launch_fwd<false, 2>(a, nblocks, c, queue) : launch_fwd<false, 1>(a, nblocks, c, queue);
+}
+
+template <int PPL>
+static cudaError_t launch_bwd(const GsrBwdArgs& a, int nblocks, const CompPtrs& c, uint32_t* queue, float* dgeom) {
+    const int smem = (int)sizeof(SmemRing);
+    cudaError_t e = cudaFuncSetAttribute(composite_bwd_kernel<PPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    composite_bwd_kernel<PPL><<<nblocks, 256 / PPL, smem, a.stream>>>(
+        a.prm.image_height, a.prm.image_width, c.grid.gx, c.grid.ntiles, c.header, c.work_order, c.tile_start,
+        c.keys, c.geom, a.prm.bg, queue, a.out_depth_alpha, c.n_contrib, a.dL_dcolor, a.dL_ddepth_alpha, dgeom);
     return cudaGetLastError();
 }
 
 cudaError_t gsr_launch_composite_bwd(const GsrBwdArgs& a) {
-    const GsrTileGrid grid = gsr_grid(a.prm.image_height, a.prm.image_width);
-    if (grid.ntiles == 0) return cudaSuccess;
-    const uint32_t* header = reinterpret_cast<const uint32_t*>(a.saved + a.vl.header);
-    const uint32_t* tile_start = reinterpret_cast<const uint32_t*>(a.saved + a.vl.tile_start);
-    const uint32_t* work_order = reinterpret_cast<const uint32_t*>(a.saved + a.vl.work_order);
-    const GsrRec* records = reinterpret_cast<const GsrRec*>(a.saved + a.vl.records);
-    const uint32_t* n_contrib = reinterpret_cast<const uint32_t*>(a.saved + a.vl.n_contrib);
+    const CompPtrs c = comp_ptrs(a.saved, a.vl, a.prm.image_height, a.prm.image_width);
+    if (c.grid.ntiles == 0) return cudaSuccess;
     uint32_t* queue = reinterpret_cast<uint32_t*>(a.scratch + a.sl.counters) + GSR_C_BWD_QUEUE;
     float* dgeom = reinterpret_cast<float*>(a.scratch + a.sl.dgeom);
-    const int smem = (int)sizeof(SmemRing);
-    const int nblocks = min(grid.ntiles, g_num_sms() * 4);
-    cudaError_t e = cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    composite_bwd_kernel<<<nblocks, kThreads, smem, a.stream>>>(
-        a.prm.image_height, a.prm.image_width, grid.gx, grid.ntiles, header, work_order, tile_start, records,
-        a.prm.bg, queue, a.out_depth_alpha, n_contrib, a.dL_dcolor, a.dL_ddepth_alpha, dgeom);
-    return cudaGetLastError();
+    const int nblocks = min(c.grid.ntiles, g_num_sms() * 4);
+    return g_ppl() == 2 ? launch_bwd<2>(a, nblocks, c, queue, dgeom) : launch_bwd<1>(a, nblocks, c, queue, dgeom);
 }

@@ -630,7 +630,7 @@ cudaError_t gsr_launch_project(const GsrFwdArgs& a) {
     project_sh_kernel<<<(P + kBlock - 1) / kBlock, kBlock, smem, a.stream>>>(
         a.prm, a.means3D, a.shs, a.colors, a.opac, a.scales, a.rots, a.cov3d, a.radii,
         reinterpret_cast<uint4*>(a.scratch + a.sl.rectdepth),
-        reinterpret_cast<GsrRec*>(a.scratch + a.sl.geom),
+        reinterpret_cast<GsrRec*>(a.saved + a.vl.geom),
         reinterpret_cast<uint32_t*>(a.scratch + a.sl.tile_count));
     return cudaGetLastError();
 }

@@ -70,7 +70,8 @@ typedef struct b200gsr_saved_layout {
     size_t tile_start;    /* uint32[num_tiles+1] exclusive prefix of per-tile pair counts */
     size_t work_order;    /* uint32[num_tiles] tile ids, longest list first */
     size_t n_contrib;     /* uint32[H*W] index(1-based) of the last blended entry per pixel */
-    size_t records;       /* 48-byte records [max_pairs], tile-major, depth-sorted (see common.cuh) */
+    size_t keys;          /* uint64[max_pairs+2] (depth_bits<<32 | gaussian idx), tile-major, depth-sorted */
+    size_t geom;          /* 48-byte per-Gaussian records [P] (see common.cuh), gathered by the composite kernels */
     size_t total;
 } b200gsr_saved_layout;
 
@@ -80,8 +81,6 @@ typedef struct b200gsr_scratch_layout {
     size_t tile_count;    /* uint32[16][num_tiles] privatised per-tile pair counters */
     size_t tile_cursor;   /* uint32[16][num_tiles] write cursors */
     size_t rectdepth;     /* uint4[P]: (minx|miny<<16, maxx|maxy<<16, depth bits, tiles touched) */
-    size_t geom;          /* 48-byte records [P] in Gaussian order */
-    size_t keys;          /* uint64[max_pairs] (depth_bits<<32 | idx), tile-major, unsorted->sorted */
     size_t dgeom;         /* backward only: float[P*12] screen-space gradient accumulators */
     size_t total;
 } b200gsr_scratch_layout;

@@ -48,10 +48,11 @@ def decode_saved(saved: torch.Tensor, P, H, W, cap):
     wo = raw[vl.work_order:vl.work_order + 4 * ntiles].view(np.uint32).astype(np.int64)
     nc = raw[vl.n_contrib:vl.n_contrib + 4 * H * W].view(np.uint32).reshape(H, W)
     n = min(D, cap)
-    rec = raw[vl.records:vl.records + 48 * n].view(np.uint32).reshape(n, 12)
+    keys = raw[vl.keys:vl.keys + 8 * n].view(np.uint64)
+    geom = raw[vl.geom:vl.geom + 48 * P].view(np.uint32).reshape(P, 12)
     return dict(num_pairs=D, header=header.copy(), tile_start=ts, work_order=wo, n_contrib=nc,
-                idx=rec[:, 11].astype(np.int64), depth_bits=rec[:, 7].copy(),
-                rec_f32=rec.view(np.float32))
+                idx=(keys & np.uint64(0xFFFFFFFF)).astype(np.int64),
+                depth_bits=(keys >> np.uint64(32)).astype(np.uint32), geom_f32=geom.view(np.float32))
 
 
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
