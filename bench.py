@@ -124,7 +124,9 @@ def cpu_oracle_step(wl, view, sample_stride=64, threads=None):
     """Full per-Gaussian stages on all P Gaussians + blending fwd/bwd on every `sample_stride`-th
     tile (ordered by list length), scaled to the full frame by (tile,Gaussian)-pair count."""
     from oracle import splat_ref as O
-    threads = threads or os.cpu_count()
+    # all host cores up to 32: beyond that PyTorch's intra-op pool only adds contention for these
+    # op sizes (measured on the 128-core box: 128 threads 5127 s/step vs 32 threads far less)
+    threads = threads or int(os.environ.get("BENCH_CPU_THREADS", min(os.cpu_count() or 1, 32)))
     torch.set_num_threads(threads)
     sc, cam, gc, gd = make_scene(wl, view)
     S = O.Settings(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy, torch.ones(3), 1.0,
@@ -311,29 +313,43 @@ def main():
         h2d = sum(host[k].numel() * 4 for k in names) + (16 + 16 + 3 + 3) * 4
         d2h = sum(v.numel() * 4 for v in out_host.values()) + sum(v.numel() * 4 for v in grad_host.values())
 
-        def e2e_step():
-            p = {k: host[k].to(dev, non_blocking=True).requires_grad_(True) for k in names}
-            color, radii_, da = step(p)
-            out_host["color"].copy_(color.detach(), non_blocking=True)
-            out_host["da"].copy_(da.detach(), non_blocking=True)
-            out_host["radii"].copy_(radii_, non_blocking=True)
-            for k in names:
-                grad_host[k].copy_(p[k].grad, non_blocking=True)
-            torch.cuda.current_stream(dev).synchronize()   # the caller owns host results after this
+        streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+        outs = [dict(out_host), {k: torch.empty_like(v).pin_memory() for k, v in out_host.items()}]
+        gouts = [dict(grad_host), {k: torch.empty_like(v).pin_memory() for k, v in grad_host.items()}]
 
-        for _ in range(2):
-            e2e_step()
+        def e2e_step(i):
+            # every step: H2D of all inputs from pinned memory, forward+backward through the public
+            # API, D2H of the rendered maps and of every parameter gradient.  Steps alternate between
+            # two streams so one step's D2H overlaps the next step's H2D; a stream is only reused
+            # after its previous step has fully completed (host results owned by the caller).
+            st = streams[i & 1]
+            st.synchronize()
+            with torch.cuda.stream(st):
+                p = {k: host[k].to(dev, non_blocking=True).requires_grad_(True) for k in names}
+                color, radii_, da = step(p)
+                oh, gh = outs[i & 1], gouts[i & 1]
+                oh["color"].copy_(color.detach(), non_blocking=True)
+                oh["da"].copy_(da.detach(), non_blocking=True)
+                oh["radii"].copy_(radii_, non_blocking=True)
+                for k in names:
+                    gh[k].copy_(p[k].grad, non_blocking=True)
+
+        for i in range(2):
+            e2e_step(i)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
+        for i in range(args.steps):
+            e2e_step(i)
+        for st in streams:
+            st.synchronize()
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e_ms = float(dt.item()) * 1e3 / args.steps
         e2e = {"value": world * H * W / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "note": "two streams: D2H of step i overlaps H2D of step i+1"}
     clk = clocks.stop() if rank == 0 else None
 
     if rank == 0:
