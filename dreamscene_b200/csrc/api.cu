@@ -101,7 +101,7 @@ int b200gsr_scratch_layout_query(int32_t P, int32_t H, int32_t W, uint64_t max_p
     if (max_pairs > 0xfffffff0ull) return fail(B200GSR_ERR_UNSUPPORTED, "max_pairs must fit in 32 bits");
     const GsrTileGrid g = gsr_grid(H, W);
     size_t off = 0;
-    out->counters = off;    off = align_up(off + 16 * sizeof(uint32_t));
+    out->counters = off;    off = align_up(off + GSR_NCOUNTERS * sizeof(uint32_t));
     out->tile_count = off;  off = align_up(off + (size_t)GSR_COPIES * g.ntiles * sizeof(uint32_t));
     out->tile_cursor = off; off = align_up(off + (size_t)GSR_COPIES * g.ntiles * sizeof(uint32_t));
     out->rectdepth = off;   off = align_up(off + (size_t)P * sizeof(uint4));
@@ -187,7 +187,7 @@ int b200gsr_backward(const b200gsr_params* prm, const float* means3D, const floa
     a.d_opac = d_opacities; a.d_scales = d_scales; a.d_rots = d_rotations; a.d_cov3d = d_cov3D;
     a.stream = static_cast<cudaStream_t>(stream);
 
-    if ((rc = check_cuda(cudaMemsetAsync(a.scratch + a.sl.counters, 0, 16 * sizeof(uint32_t), a.stream), "memset"))) return rc;
+    if ((rc = check_cuda(cudaMemsetAsync(a.scratch + a.sl.counters, 0, GSR_NCOUNTERS * sizeof(uint32_t), a.stream), "memset"))) return rc;
     if ((rc = check_cuda(cudaMemsetAsync(a.scratch + a.sl.dgeom, 0, (size_t)prm->P * 12 * sizeof(float), a.stream), "memset"))) return rc;
     prof_mark_bwd(0, a.stream);
     if ((rc = check_cuda(gsr_launch_composite_bwd(a), "composite_bwd"))) return rc;

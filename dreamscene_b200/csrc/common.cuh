@@ -49,7 +49,11 @@ __host__ __device__ inline GsrTileGrid gsr_grid(int H, int W) {
 enum { GSR_H_NUM_PAIRS = 0, GSR_H_MAX_PAIRS = 1, GSR_H_NUM_TILES = 2, GSR_H_OVERFLOW = 3,
        GSR_H_NUM_BIG = 4, GSR_H_NUM_NONEMPTY = 5 };
 // counters in scratch
-enum { GSR_C_FWD_QUEUE = 0, GSR_C_BWD_QUEUE = 1, GSR_C_SORT_SMALL = 2, GSR_C_SORT_BIG = 3 };
+// The tile work queue is split into GSR_NQUEUE sub-queues (tile w lives in queue w % NQUEUE): one
+// shared counter would serialise every fetch at the ~30 ns same-address L2 atomic rate.
+#define GSR_NQUEUE 32
+#define GSR_NCOUNTERS 128
+enum { GSR_C_FWD_QUEUE = 0, GSR_C_BWD_QUEUE = GSR_NQUEUE };
 
 #define GSR_SORT_SMALL_MAX 4096   // keys sorted by the 256-thread kernel (256 x 16 items)
 #define GSR_SORT_BIG_CHUNK 16384  // keys per smem chunk of the 1024-thread kernel (1024 x 16 items)
@@ -124,6 +128,22 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  : "memory");
 }
 #endif  // __CUDACC__
+
+#ifdef __CUDACC__
+// Fetch the next work item (index into the longest-first work order, < limit) from the split
+// queue; returns false when every sub-queue is exhausted.  Call from one thread.
+__device__ __forceinline__ bool gsr_queue_pop(uint32_t* counters, uint32_t limit, uint32_t& q, uint32_t& tried,
+                                              uint32_t& item) {
+    while (tried < GSR_NQUEUE) {
+        const uint32_t i = atomicAdd(counters + q, 1u);
+        const uint32_t w = i * GSR_NQUEUE + q;
+        if (w < limit) { item = w; return true; }
+        q = (q + 1) % GSR_NQUEUE;
+        ++tried;
+    }
+    return false;
+}
+#endif
 
 // ---- kernel launchers (defined in the .cu files, called from api.cu) ---------------------
 struct GsrFwdArgs {

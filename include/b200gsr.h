@@ -77,7 +77,7 @@ typedef struct b200gsr_saved_layout {
 
 /* Byte offsets inside the transient `scratch` buffer (valid until the next call on the stream). */
 typedef struct b200gsr_scratch_layout {
-    size_t counters;      /* uint32[16] work-queue counters */
+    size_t counters;      /* uint32[128] split work-queue counters */
     size_t tile_count;    /* uint32[16][num_tiles] privatised per-tile pair counters */
     size_t tile_cursor;   /* uint32[16][num_tiles] write cursors */
     size_t rectdepth;     /* uint4[P]: (minx|miny<<16, maxx|maxy<<16, depth bits, tiles touched) */

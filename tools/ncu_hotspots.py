@@ -15,6 +15,7 @@ import tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, kern, unit = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
+BY_STALL = os.environ.get("BY_STALL") == "1"   # rank lines by stall samples instead of instructions
 so = os.path.join(ROOT, "dreamscene_b200", "libb200gsr.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", f"{unit}.sm_100a.cubin", so], cwd=tmp, check=True, capture_output=True)
@@ -57,7 +58,9 @@ for a, n, s in ins:
 tot, ts = sum(agg.values()), sum(samp.values())
 srcs = {}
 print(f"kernel {t['name'][:80]}\n total warp instructions {tot}, stall samples {ts}")
-for ln, n in agg.most_common(top):
+order = samp.most_common(top) if BY_STALL else agg.most_common(top)
+for ln, _ in order:
+    n = agg[ln]
     if ln[0] not in srcs:
         p = os.path.join(ROOT, "dreamscene_b200", "csrc", ln[0])
         srcs[ln[0]] = open(p).read().splitlines() if os.path.exists(p) else []
