@@ -180,22 +180,36 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-// half a warp per row, two rows per iteration
+// MT > 0: M known at compile time (16 = objects, 4 = scenes) -> the block's rows are one contiguous
+// span of kBlock*3M floats that the threads copy as a flat sequence of 16-B units (perfectly
+// coalesced, constant-divisor index math).  MT == 0: generic M (half a warp per row).
+template <int MT>
 __device__ __forceinline__ void stage_sh_rows(const float* __restrict__ shs, int M, int nf, int g0, int P,
                                               const uint8_t* vis, float* buf, int stride) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int hl = lane & 15, hsel = lane >> 4;
-    const bool vec = ((3 * M) & 3) == 0;
     const int nchunk = (nf + 3) >> 2;
-    for (int it = 0; it < kBlock / 8; ++it) {
-        const int row = it * 8 + w * 2 + hsel;          // 4 warps x 2 rows per iteration
-        if (g0 + row < P && vis[row]) {
-            const float* src = shs + (size_t)(g0 + row) * 3 * M;
-            float* dst = buf + row * stride;
-            if (vec) {
-                if (hl < nchunk) cp_async16(dst + 4 * hl, src + 4 * hl);
-            } else {
-                for (int col = hl; col < nf; col += 16) cp_async4(dst + col, src + col);
+    if (MT > 0 && ((3 * MT) & 3) == 0) {
+        constexpr int q4 = (3 * (MT > 0 ? MT : 4)) / 4;   // 16-B units per row
+        const float* base = shs + (size_t)g0 * 3 * MT;
+#pragma unroll
+        for (int it = 0; it < q4; ++it) {
+            const int u = it * kBlock + threadIdx.x;
+            const int row = u / q4, c4 = u - row * q4;
+            if (c4 < nchunk && g0 + row < P && vis[row]) cp_async16(buf + row * stride + 4 * c4, base + 4 * u);
+        }
+    } else {
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        const int hl = lane & 15, hsel = lane >> 4;
+        const bool vec = ((3 * M) & 3) == 0;
+        for (int it = 0; it < kBlock / 8; ++it) {
+            const int row = it * 8 + w * 2 + hsel;          // 4 warps x 2 rows per iteration
+            if (g0 + row < P && vis[row]) {
+                const float* src = shs + (size_t)(g0 + row) * 3 * M;
+                float* dst = buf + row * stride;
+                if (vec) {
+                    if (hl < nchunk) cp_async16(dst + 4 * hl, src + 4 * hl);
+                } else {
+                    for (int col = hl; col < nf; col += 16) cp_async4(dst + col, src + col);
+                }
             }
         }
     }
@@ -247,6 +261,7 @@ __device__ __forceinline__ void sh_color(const float (&B)[16], const float* row,
 // =========================================================================================
 // Forward: one Gaussian per thread, kBlock Gaussians per CTA.
 // =========================================================================================
+template <int MT>
 __global__ void __launch_bounds__(kBlock)
 project_sh_kernel(b200gsr_params p, const float* __restrict__ means3D,
                   const float* __restrict__ shs, const float* __restrict__ colors,
@@ -305,7 +320,7 @@ project_sh_kernel(b200gsr_params p, const float* __restrict__ means3D,
     if (shs != nullptr) {
         vis_s[threadIdx.x] = vis;
         __syncthreads();
-        stage_sh_rows(shs, p.M, 3 * ncoef, g0, p.P, vis_s, sh_buf, stride);
+        stage_sh_rows<MT>(shs, p.M, 3 * ncoef, g0, p.P, vis_s, sh_buf, stride);
         __syncthreads();
     }
     if (!vis) return;
@@ -359,7 +374,8 @@ project_sh_kernel(b200gsr_params p, const float* __restrict__ means3D,
 //   2: sum g*dx*dx  3: sum g*dx*dy  4: sum g*dy*dy
 //   5: sum G*dL/dalpha (dL/dopacity)   6..8: dL/drgb   9: dL/ddepth   10,11: unused
 // =========================================================================================
-__global__ void __launch_bounds__(kBlock)
+template <int MT>
+__global__ void __launch_bounds__(kBlock, 8)
 project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
                    const float* __restrict__ shs, const float* __restrict__ colors,
                    const float* __restrict__ scales, const float* __restrict__ rots,
@@ -382,7 +398,7 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
     if (shs != nullptr) {
         vis_s[threadIdx.x] = vis;
         __syncthreads();
-        stage_sh_rows(shs, p.M, 3 * ncoef, g0, p.P, vis_s, sh_buf, stride);
+        stage_sh_rows<MT>(shs, p.M, 3 * ncoef, g0, p.P, vis_s, sh_buf, stride);
         __syncthreads();
     }
     float dmean[3] = {0.f, 0.f, 0.f};
@@ -589,24 +605,39 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
     if (shs != nullptr) {
         // drain the rows with coalesced stores (zeros for culled rows / inactive degrees)
         __syncthreads();
-        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-        const int hl = lane & 15, hsel = lane >> 4;
         const int nf = 3 * ncoef, nchunk = (nf + 3) >> 2;
-        const bool vec = (nsh & 3) == 0;
-        for (int it = 0; it < kBlock / 8; ++it) {
-            const int row = it * 8 + w * 2 + hsel;
-            if (g0 + row >= p.P) continue;
-            float* dst = d_shs + (size_t)(g0 + row) * nsh;
-            const bool v = vis_s[row];
-            if (vec) {
-                for (int q = hl; 4 * q < nsh; q += 16) {
+        if (MT > 0 && ((3 * MT) & 3) == 0) {
+            constexpr int q4 = (3 * (MT > 0 ? MT : 4)) / 4;
+            float* base = d_shs + (size_t)g0 * 3 * MT;
+#pragma unroll
+            for (int it = 0; it < q4; ++it) {
+                const int u = it * kBlock + threadIdx.x;
+                const int row = u / q4, c4 = u - row * q4;
+                if (g0 + row < p.P) {
                     float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (v && q < nchunk) val = *reinterpret_cast<const float4*>(sh_buf + row * stride + 4 * q);
-                    stg_na_f4(dst + 4 * q, val);
+                    if (c4 < nchunk && vis_s[row]) val = *reinterpret_cast<const float4*>(sh_buf + row * stride + 4 * c4);
+                    stg_na_f4(base + 4 * u, val);
                 }
-            } else {
-                for (int col = hl; col < nsh; col += 16)
-                    dst[col] = (v && col < nf) ? sh_buf[row * stride + col] : 0.0f;
+            }
+        } else {
+            const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+            const int hl = lane & 15, hsel = lane >> 4;
+            const bool vec = (nsh & 3) == 0;
+            for (int it = 0; it < kBlock / 8; ++it) {
+                const int row = it * 8 + w * 2 + hsel;
+                if (g0 + row >= p.P) continue;
+                float* dst = d_shs + (size_t)(g0 + row) * nsh;
+                const bool v = vis_s[row];
+                if (vec) {
+                    for (int q = hl; 4 * q < nsh; q += 16) {
+                        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (v && q < nchunk) val = *reinterpret_cast<const float4*>(sh_buf + row * stride + 4 * q);
+                        stg_na_f4(dst + 4 * q, val);
+                    }
+                } else {
+                    for (int col = hl; col < nsh; col += 16)
+                        dst[col] = (v && col < nf) ? sh_buf[row * stride + col] : 0.0f;
+                }
             }
         }
     }
@@ -623,26 +654,40 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
 
 }  // namespace
 
-cudaError_t gsr_launch_project(const GsrFwdArgs& a) {
-    const int P = a.prm.P;
-    if (P == 0) return cudaSuccess;
-    const size_t smem = a.shs ? (size_t)kBlock * sh_row_stride(a.prm.M) * sizeof(float) : 0;
-    project_sh_kernel<<<(P + kBlock - 1) / kBlock, kBlock, smem, a.stream>>>(
+template <int MT>
+static void launch_project_sh(const GsrFwdArgs& a, int P, size_t smem) {
+    project_sh_kernel<MT><<<(P + kBlock - 1) / kBlock, kBlock, smem, a.stream>>>(
         a.prm, a.means3D, a.shs, a.colors, a.opac, a.scales, a.rots, a.cov3d, a.radii,
         reinterpret_cast<uint4*>(a.scratch + a.sl.rectdepth),
         reinterpret_cast<GsrRec*>(a.saved + a.vl.geom),
         reinterpret_cast<uint32_t*>(a.scratch + a.sl.tile_count));
+}
+
+cudaError_t gsr_launch_project(const GsrFwdArgs& a) {
+    const int P = a.prm.P;
+    if (P == 0) return cudaSuccess;
+    const size_t smem = a.shs ? (size_t)kBlock * sh_row_stride(a.prm.M) * sizeof(float) : 0;
+    if (a.shs && a.prm.M == 16) launch_project_sh<16>(a, P, smem);
+    else if (a.shs && a.prm.M == 4) launch_project_sh<4>(a, P, smem);
+    else launch_project_sh<0>(a, P, smem);
     return cudaGetLastError();
+}
+
+template <int MT>
+static void launch_project_bwd(const GsrBwdArgs& a, int P, size_t smem) {
+    project_bwd_kernel<MT><<<(P + kBlock - 1) / kBlock, kBlock, smem, a.stream>>>(
+        a.prm, a.means3D, a.shs, a.colors, a.scales, a.rots, a.cov3d, a.radii,
+        reinterpret_cast<const float*>(a.scratch + a.sl.dgeom), a.d_means3D, a.d_means2D, a.d_shs,
+        a.d_colors, a.d_opac, a.d_scales, a.d_rots, a.d_cov3d);
 }
 
 cudaError_t gsr_launch_project_bwd(const GsrBwdArgs& a) {
     const int P = a.prm.P;
     if (P == 0) return cudaSuccess;
     const size_t smem = a.shs ? (size_t)kBlock * sh_row_stride(a.prm.M) * sizeof(float) : 0;
-    project_bwd_kernel<<<(P + kBlock - 1) / kBlock, kBlock, smem, a.stream>>>(
-        a.prm, a.means3D, a.shs, a.colors, a.scales, a.rots, a.cov3d, a.radii,
-        reinterpret_cast<const float*>(a.scratch + a.sl.dgeom), a.d_means3D, a.d_means2D, a.d_shs,
-        a.d_colors, a.d_opac, a.d_scales, a.d_rots, a.d_cov3d);
+    if (a.shs && a.prm.M == 16) launch_project_bwd<16>(a, P, smem);
+    else if (a.shs && a.prm.M == 4) launch_project_bwd<4>(a, P, smem);
+    else launch_project_bwd<0>(a, P, smem);
     return cudaGetLastError();
 }
 
