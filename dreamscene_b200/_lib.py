@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "libb200gsr.so")
 EXPORTS = ["b200gsr_version", "b200gsr_last_error", "b200gsr_saved_layout_query",
            "b200gsr_scratch_layout_query", "b200gsr_forward", "b200gsr_backward",
            "b200gsr_mark_visible", "b200gsr_profile_enable", "b200gsr_profile_counts",
-           "b200gsr_profile_read"]
+           "b200gsr_profile_read", "b200gsr_dist2_scratch_bytes", "b200gsr_dist2_knn3"]
 
 
 class Params(C.Structure):
@@ -55,6 +55,10 @@ def load():
     lib.b200gsr_backward.argtypes = [C.POINTER(Params)] + [vp] * 7 + [vp] * 4 + \
         [vp, sz, vp, sz, u64] + [vp] * 8 + [vp]
     lib.b200gsr_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]
+    lib.b200gsr_dist2_scratch_bytes.argtypes = [i32]
+    lib.b200gsr_dist2_scratch_bytes.restype = C.c_size_t
+    lib.b200gsr_dist2_knn3.argtypes = [i32, vp, vp, vp, sz, vp]
+    lib.b200gsr_dist2_knn3.restype = C.c_int
     lib.b200gsr_profile_enable.argtypes = [i32]
     lib.b200gsr_profile_counts.argtypes = [C.POINTER(i32), C.POINTER(i32)]
     lib.b200gsr_profile_read.argtypes = [i32, i32, C.POINTER(C.c_float)]

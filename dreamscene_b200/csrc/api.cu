@@ -234,6 +234,19 @@ int b200gsr_profile_read(int32_t is_backward, int32_t call, float* ms) {
     return B200GSR_OK;
 }
 
+size_t b200gsr_dist2_scratch_bytes(int32_t P) { return P < 0 ? 0 : gsr_knn_scratch_bytes(P, nullptr); }
+
+int b200gsr_dist2_knn3(int32_t P, const float* points, float* out, void* scratch, size_t scratch_bytes,
+                       void* stream) {
+    if (P < 0 || (P > 0 && (!points || !out || !scratch)))
+        return fail(B200GSR_ERR_BAD_ARG, "bad dist2_knn3 arguments");
+    if (scratch_bytes < gsr_knn_scratch_bytes(P, nullptr))
+        return fail(B200GSR_ERR_WORKSPACE, "dist2_knn3 scratch too small: %zu < %zu", scratch_bytes,
+                    gsr_knn_scratch_bytes(P, nullptr));
+    return check_cuda(gsr_launch_knn(P, points, out, static_cast<uint8_t*>(scratch), static_cast<cudaStream_t>(stream)),
+                      "dist2_knn3");
+}
+
 int b200gsr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
                          const float* projmatrix, uint8_t* visible, void* stream) {
     if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !visible)))

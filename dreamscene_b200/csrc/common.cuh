@@ -183,3 +183,7 @@ cudaError_t gsr_launch_composite_bwd(const GsrBwdArgs& a);
 cudaError_t gsr_launch_project_bwd(const GsrBwdArgs& a);
 cudaError_t gsr_launch_mark_visible(int P, const float* means3D, const float* view,
                                     const float* proj, uint8_t* visible, cudaStream_t s);
+
+// simple_knn replacement (knn.cu)
+size_t gsr_knn_scratch_bytes(int P, int* max_cells_out);
+cudaError_t gsr_launch_knn(int P, const float* pts, float* out, uint8_t* scratch, cudaStream_t s);

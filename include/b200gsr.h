@@ -139,6 +139,15 @@ int b200gsr_mark_visible(int32_t P, const float* means3D, const float* viewmatri
                          const float* projmatrix, uint8_t* visible, void* stream);
 
 /*
+ * replaces simple_knn._C.distCUDA2 (un-vendored; /root/reference/gs_renderer.py:9,590-593):
+ * out[i] = mean of the squared distances from points[i] to its 3 nearest OTHER points (points f32[P,3]).
+ * `scratch` = b200gsr_dist2_scratch_bytes(P) bytes of device memory.
+ */
+size_t b200gsr_dist2_scratch_bytes(int32_t P);
+int b200gsr_dist2_knn3(int32_t P, const float* points, float* out, void* scratch, size_t scratch_bytes,
+                       void* stream);
+
+/*
  * Optional per-stage device timing for benchmarks (no upstream equivalent).  Process-wide and not
  * thread-safe.  enable(max_calls>0) allocates CUDA events; every later forward/backward call
  * (up to max_calls each) records events around its stages on the call's stream; read() waits for
