@@ -131,6 +131,8 @@ def _forward_impl(rs, means3D, shs, colors, opac, scales, rots, cov3d):
     ws = _workspace(dev)
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     cap = ws.capacity if ws.capacity > 0 else _round_cap(6 * P)
+    if torch.cuda.current_device() != dev.index:
+        torch.cuda.set_device(dev)        # the library launches on the CURRENT device (callers use cuda:0)
     while True:
         sl = _lib.scratch_layout(P, H, W, cap)
         vl = _lib.saved_layout(P, H, W, cap)
@@ -231,6 +233,8 @@ class _RasterizeGaussians(torch.autograd.Function):
 
         if P > 0:
             lib = _lib.load()
+            if torch.cuda.current_device() != dev.index:
+                torch.cuda.set_device(dev)
             keep: list = []
             prm = _make_params(rs, P, M, keep)
             ws = _workspace(dev)
