@@ -251,6 +251,37 @@ def test_equal_depth_runs_and_skewed_depths_sort_exactly():
     check_images(cu, ref)
 
 
+def test_screen_filling_gaussians_scale_modifier_and_score():
+    """A few huge Gaussians (tile rect = whole image, thousands of tiles each) mixed with small ones,
+    scale_modifier != 1, score_flag on, 1080p-like aspect with partial tiles."""
+    H, W = 135, 240
+    sc, cam, deg = U.make_inputs(3000, H, W, seed=29)
+    sc["scales"][:5] = 2.0                      # bigger than the scene: cover every tile
+    sc["opacities"][:5] = 0.3
+    g = torch.Generator().manual_seed(3)
+    grads = (torch.randn(3, H, W, generator=g) / (H * W), torch.randn(2, H, W, generator=g) / (H * W))
+    ref32 = run_oracle(sc, cam, deg, score=True, scale_modifier=0.7)
+    assert int(ref32["pre"]["touched"].max()) == ((H + 15) // 16) * ((W + 15) // 16)
+    ref = run_oracle(sc, cam, deg, grads=grads, dtype=torch.float64, decisions=ref32["decisions"], scale_modifier=0.7)
+    cu = run_cuda(sc, cam, deg, score=True, grads=grads, scale_modifier=0.7)
+    np.testing.assert_array_equal(cu["radii"].cpu().numpy(), ref32["radii"].numpy())
+    check_images(cu, ref32)
+    assert U.rel_err(cu["score"], ref32["score"]) < 1e-4
+    for k in ("means3D", "scales", "rotations", "opacities", "shs", "means2D"):
+        assert U.rel_err(cu["grads"][k], ref["grads"][k]) < 1e-3, k
+
+
+def test_single_gaussian_and_random_background():
+    sc, cam, deg = U.make_inputs(1, 64, 64, seed=31, scale_mul=30.0)
+    sc["means3D"][:] = 0.0
+    bg = (0.1, 0.7, 0.4)
+    ref = run_oracle(sc, cam, deg, bg=bg)
+    cu = run_cuda(sc, cam, deg, bg=bg, grads=(torch.ones(3, 64, 64), torch.zeros(2, 64, 64)))
+    assert int(cu["radii"][0]) == int(ref["radii"][0]) > 0
+    check_images(cu, ref)
+    assert torch.isfinite(cu["grads"]["means3D"]).all()
+
+
 def test_api_errors_match_reference_messages():
     from dreamscene_b200 import GaussianRasterizer
     sc, cam, deg = U.make_inputs(16, 32, 32)
