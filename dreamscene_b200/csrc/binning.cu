@@ -126,7 +126,7 @@ scatter_kernel(int P, int gx, int ntiles, uint32_t max_pairs, const uint4* __res
     if (i >= P) return;
     const uint4 rd = __ldg(rectdepth + i);
     if (rd.w == 0) return;
-    const int minx = rd.x & 0xffff, miny = rd.x >> 16, maxx = rd.y & 0xffff, maxy = rd.y >> 16;
+    const int minx = rd.x & 0xffff, miny = rd.x >> 16, maxx = rd.y & 0xffff;
     const unsigned long long key = ((unsigned long long)rd.z << 32) | (uint32_t)i;
     uint32_t* cur = tile_cursor + (size_t)((i >> 5) & (GSR_COPIES - 1)) * ntiles;
     // The returned atomics are issued in batches of 8 before any dependent store, so up to 8

@@ -16,8 +16,8 @@
 // One (tile, Gaussian) pair as consumed by the composite kernels; also the per-Gaussian
 // "geom" record written by project_sh (the sort epilogue copies geom[idx] -> sorted[pos]).
 // 48 bytes = 3 x 16 B, so 8 consecutive lanes reading one 16-B part each hit 8 distinct
-// 4-bank groups (stride 12 words) -> conflict-free LDS.128, and tile lists are contiguous
-// 16-B-aligned byte ranges -> one cp.async.bulk (TMA) per chunk.
+// 4-bank groups (stride 12 words) -> conflict-free LDS.128, and a record moves as three
+// 16-byte cp.async copies.
 struct __align__(16) GsrRec {
     // part 0: everything the per-warp cull test needs
     float px, py;   // pixel-space mean
@@ -63,25 +63,11 @@ enum { GSR_C_FWD_QUEUE = 0, GSR_C_BWD_QUEUE = GSR_NQUEUE };
 
 #ifdef __CUDACC__
 // ---- 128-bit global access helpers -------------------------------------------------------
-__device__ __forceinline__ float4 ldg_nc_f4(const void* p) {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
 __device__ __forceinline__ float4 ldg_f4(const void* p) {
     return *reinterpret_cast<const float4*>(p);
 }
-__device__ __forceinline__ void stg_f4(void* p, float4 v) {
-    *reinterpret_cast<float4*>(p) = v;
-}
 __device__ __forceinline__ void stg_na_f4(void* p, float4 v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
-                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ void red_add_f4(float* p, float4 v) {
-    // sm_90+: one 16-byte vector reduction instead of four scalar REDs
-    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -95,37 +81,9 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 
-// ---- mbarrier + bulk async copy (TMA 1-D) -------------------------------------------------
+// ---- shared-memory address helper (cp.async destinations) ----------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_fence_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                 "selp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {}
-}
-// global -> shared bulk copy, completion counted on an mbarrier (SASS: UBLKCP.S.G)
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
-                                         uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
 }
 #endif  // __CUDACC__
 
