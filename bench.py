@@ -314,29 +314,32 @@ def main():
         h2d = sum(host[k].numel() * 4 for k in names) + (16 + 16 + 3 + 3) * 4
         d2h = sum(v.numel() * 4 for v in out_host.values()) + sum(v.numel() * 4 for v in grad_host.values())
 
-        streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
-        outs = [dict(out_host), {k: torch.empty_like(v).pin_memory() for k, v in out_host.items()}]
-        gouts = [dict(grad_host), {k: torch.empty_like(v).pin_memory() for k, v in grad_host.items()}]
+        NS = 3   # steps in flight: H2D of step i+1/i+2 overlaps compute and D2H of step i (full-duplex PCIe)
+        streams = [torch.cuda.Stream(dev) for _ in range(NS)]
+        outs = [dict(out_host)] + [{k: torch.empty_like(v).pin_memory() for k, v in out_host.items()} for _ in range(NS - 1)]
+        gouts = [dict(grad_host)] + [{k: torch.empty_like(v).pin_memory() for k, v in grad_host.items()} for _ in range(NS - 1)]
 
         def e2e_step(i):
             # every step: H2D of all inputs from pinned memory, forward+backward through the public
-            # API, D2H of the rendered maps and of every parameter gradient.  Steps alternate between
-            # two streams so one step's D2H overlaps the next step's H2D; a stream is only reused
-            # after its previous step has fully completed (host results owned by the caller).
-            st = streams[i & 1]
+            # API, D2H of the rendered maps and of every parameter gradient.  Steps rotate over NS
+            # streams so one step's D2H overlaps the next steps' H2D; a stream is only reused after
+            # its previous step has fully completed (host results owned by the caller).
+            st = streams[i % NS]
             st.synchronize()
             with torch.cuda.stream(st):
                 p = {k: host[k].to(dev, non_blocking=True).requires_grad_(True) for k in names}
                 color, radii_, da = step(p)
-                oh, gh = outs[i & 1], gouts[i & 1]
+                oh, gh = outs[i % NS], gouts[i % NS]
                 oh["color"].copy_(color.detach(), non_blocking=True)
                 oh["da"].copy_(da.detach(), non_blocking=True)
                 oh["radii"].copy_(radii_, non_blocking=True)
                 for k in names:
                     gh[k].copy_(p[k].grad, non_blocking=True)
 
-        for i in range(2):
+        for i in range(NS):
             e2e_step(i)
+        for st in streams:
+            st.synchronize()
         barrier()
         t0 = time.perf_counter()
         for i in range(args.steps):
@@ -350,7 +353,7 @@ def main():
         e2e_ms = float(dt.item()) * 1e3 / args.steps
         e2e = {"value": world * H * W / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "note": "two streams: D2H of step i overlaps H2D of step i+1"}
+               "note": "3 steps in flight on 3 streams: D2H of step i overlaps H2D of steps i+1, i+2"}
     clk = clocks.stop() if rank == 0 else None
 
     if rank == 0:

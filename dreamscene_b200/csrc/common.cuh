@@ -51,7 +51,7 @@ enum { GSR_H_NUM_PAIRS = 0, GSR_H_MAX_PAIRS = 1, GSR_H_NUM_TILES = 2, GSR_H_OVER
 // counters in scratch
 // The tile work queue is split into GSR_NQUEUE sub-queues (tile w lives in queue w % NQUEUE): one
 // shared counter would serialise every fetch at the ~30 ns same-address L2 atomic rate.
-#define GSR_NQUEUE 32
+#define GSR_NQUEUE 8
 #define GSR_NCOUNTERS 128
 enum { GSR_C_FWD_QUEUE = 0, GSR_C_BWD_QUEUE = GSR_NQUEUE };
 

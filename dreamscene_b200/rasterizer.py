@@ -94,7 +94,10 @@ def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
         return None
     if t.dtype != torch.float32:
         t = t.float()
-    return t.contiguous()
+    t = t.contiguous()
+    if t.data_ptr() % 16:          # the kernels use 16-byte vector loads on rows
+        t = t.clone()
+    return t
 
 
 def _make_params(rs: GaussianRasterizationSettings, P: int, M: int, keep: list) -> _lib.Params:
@@ -214,21 +217,26 @@ class _RasterizeGaussians(torch.autograd.Function):
         # one flat buffer for every parameter gradient: a single NCCL all-reduce when views are
         # sharded across ranks (dreamscene_b200.parallel), and one allocation otherwise
         n_col = 3 * M if has_sh else 3
-        n_cov = 7 if has_sr else 6
-        flat = torch.empty(P * (3 + 1 + n_col + n_cov), dtype=torch.float32, device=dev)
-        o = 0
-        d_means3D = flat[o:o + 3 * P].view(P, 3); o += 3 * P
-        d_opac = flat[o:o + P].view(P, 1); o += P
-        d_colsh = flat[o:o + n_col * P]; o += n_col * P
+        widths = [("means3D", 3), ("opac", 1), ("col", n_col)] + ([("scales", 3), ("rots", 4)] if has_sr else [("cov", 6)])
+        # every section starts on a 256-byte boundary (the kernels use 16-byte vector stores)
+        offs, o = {}, 0
+        for name, wdt in widths:
+            offs[name] = o
+            o += (P * wdt + 63) // 64 * 64
+        flat = torch.empty(max(o, 1), dtype=torch.float32, device=dev)
+        sec = lambda name, wdt: flat[offs[name]:offs[name] + P * wdt]
+        d_means3D = sec("means3D", 3).view(P, 3)
+        d_opac = sec("opac", 1).view(P, 1)
+        d_colsh = sec("col", n_col)
         d_sh = d_colsh.view(P, M, 3) if has_sh else None
         d_colors = d_colsh.view(P, 3) if has_col else None
         if has_sr:
-            d_scales = flat[o:o + 3 * P].view(P, 3); o += 3 * P
-            d_rots = flat[o:o + 4 * P].view(P, 4); o += 4 * P
+            d_scales = sec("scales", 3).view(P, 3)
+            d_rots = sec("rots", 4).view(P, 4)
             d_cov = None
         else:
             d_scales = d_rots = None
-            d_cov = flat[o:o + 6 * P].view(P, 6); o += 6 * P
+            d_cov = sec("cov", 6).view(P, 6)
         d_means2D = torch.empty(P, 3, dtype=torch.float32, device=dev)
 
         if P > 0:

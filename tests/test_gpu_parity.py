@@ -272,14 +272,40 @@ def test_screen_filling_gaussians_scale_modifier_and_score():
 
 
 def test_single_gaussian_and_random_background():
-    sc, cam, deg = U.make_inputs(1, 64, 64, seed=31, scale_mul=30.0)
+    sc, cam, deg = U.make_inputs(1, 64, 64, seed=31)
     sc["means3D"][:] = 0.0
+    sc["scales"][:] = torch.tensor([0.08, 0.05, 0.03])
+    sc["opacities"][:] = 0.8
     bg = (0.1, 0.7, 0.4)
     ref = run_oracle(sc, cam, deg, bg=bg)
     cu = run_cuda(sc, cam, deg, bg=bg, grads=(torch.ones(3, 64, 64), torch.zeros(2, 64, 64)))
     assert int(cu["radii"][0]) == int(ref["radii"][0]) > 0
     check_images(cu, ref)
     assert torch.isfinite(cu["grads"]["means3D"]).all()
+
+
+@pytest.mark.parametrize("P", [2, 3, 7, 1001])
+def test_odd_point_counts_forward_backward(P):
+    """Gradient sections of the flat buffer must stay 16-byte aligned for any P."""
+    sc, cam, deg = U.make_inputs(P, 48, 48, seed=37 + P, exact_knn=False, scale_mul=3.0)
+    g = torch.Generator().manual_seed(P)
+    grads = (torch.randn(3, 48, 48, generator=g), torch.randn(2, 48, 48, generator=g))
+    ref32 = run_oracle(sc, cam, deg)
+    ref = run_oracle(sc, cam, deg, grads=grads, dtype=torch.float64, decisions=ref32["decisions"])
+    cu = run_cuda(sc, cam, deg, grads=grads)
+    check_images(cu, ref32)
+    for k in ("means3D", "scales", "rotations", "opacities", "shs"):
+        assert U.rel_err(cu["grads"][k], ref["grads"][k]) < 1e-3, k
+    # also through an unaligned view of a larger tensor
+    from dreamscene_b200 import GaussianRasterizer
+    S = U.cuda_settings(cam, deg)
+    big = torch.zeros(P * 3 + 1, device="cuda")
+    big[1:] = sc["means3D"].reshape(-1).cuda()
+    t = {k: v.cuda() for k, v in sc.items()}
+    c2, r2, d2 = GaussianRasterizer(S)(means3D=big[1:].view(P, 3), means2D=torch.zeros(P, 3, device="cuda"),
+                                       opacities=t["opacities"], shs=t["shs"], scales=t["scales"],
+                                       rotations=t["rotations"])
+    assert torch.equal(c2.cpu(), cu["color"].cpu())
 
 
 def test_api_errors_match_reference_messages():
