@@ -42,7 +42,7 @@ WORKLOADS = {
     "cfg1_10k_256": dict(P=10_000, H=256, W=256, radius=0.5, opacity="sigmoid_normal"),
 }
 METRIC = "fwd+bwd Mpix/s @1M Gaussians/1024^2"
-KERNELS_PER_STEP = 8   # project_sh, scan_order, scatter, sort_big, sort_small, composite_fwd, composite_bwd, project_bwd
+KERNELS_PER_STEP = 9   # project_sh, multisplit<count>, scan_order, multisplit<scatter>, sort_big, sort_small, composite_fwd, composite_bwd, project_bwd
 
 
 def measured_peaks():

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200gsr.so")
+LIB_PATH = os.environ.get("B200GSR_LIB", os.path.join(HERE, "libb200gsr.so"))   # override: A/B builds only
 
 EXPORTS = ["b200gsr_version", "b200gsr_last_error", "b200gsr_saved_layout_query",
            "b200gsr_scratch_layout_query", "b200gsr_forward", "b200gsr_backward",

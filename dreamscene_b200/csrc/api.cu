@@ -141,6 +141,7 @@ int b200gsr_forward(const b200gsr_params* prm, const float* means3D, const float
     if ((rc = check_cuda(cudaMemsetAsync(a.scratch, 0, a.sl.tile_cursor, a.stream), "memset"))) return rc;
     prof_mark_fwd(0, a.stream);
     if ((rc = check_cuda(gsr_launch_project(a), "project_sh"))) return rc;
+    if ((rc = check_cuda(gsr_launch_count(a), "tile_count"))) return rc;
     prof_mark_fwd(1, a.stream);
     if ((rc = check_cuda(gsr_launch_scan(a), "scan_order"))) return rc;
     prof_mark_fwd(2, a.stream);

@@ -149,6 +149,60 @@ scatter_kernel(int P, int gx, int ntiles, uint32_t max_pairs, const uint4* __res
 }
 
 // ---------------------------------------------------------------------------------------------
+// Block multisplit (default path).  count: smem histogram of the CTA's tile hits, then ONE global
+// RED per touched tile.  scatter: same histogram again, ONE returned global atomic per touched tile
+// reserves the CTA's contiguous slice of that tile's segment, then every pair takes its slot
+// inside the slice from a shared-memory atomic.
+// ---------------------------------------------------------------------------------------------
+template <bool SCATTER>
+__global__ void __launch_bounds__(1024)
+multisplit_kernel(int P, int gx, int ntiles, uint32_t max_pairs, const uint4* __restrict__ rectdepth,
+                  uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_cursor,
+                  unsigned long long* __restrict__ keys) {
+    extern __shared__ uint32_t ms_smem[];
+    uint32_t* hist = ms_smem;            // [ntiles] counts, later in-slice cursors
+    uint32_t* base = ms_smem + ntiles;   // [ntiles] start of this CTA's slice (SCATTER only)
+    for (int t = threadIdx.x; t < ntiles; t += 1024) hist[t] = 0u;
+    __syncthreads();
+    const int i0 = blockIdx.x * (1024 * GSR_MS_ITEMS);
+    uint4 rd[GSR_MS_ITEMS];
+#pragma unroll
+    for (int u = 0; u < GSR_MS_ITEMS; ++u) {
+        const int i = i0 + u * 1024 + threadIdx.x;
+        rd[u] = (i < P) ? __ldg(rectdepth + i) : make_uint4(0u, 0u, 0u, 0u);
+        if (rd[u].w) {
+            const int minx = rd[u].x & 0xffff, miny = rd[u].x >> 16, maxx = rd[u].y & 0xffff, maxy = rd[u].y >> 16;
+            for (int ty = miny; ty < maxy; ++ty)
+                for (int tx = minx; tx < maxx; ++tx) atomicAdd(&hist[ty * gx + tx], 1u);
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < ntiles; t += 1024) {
+        const uint32_t c = hist[t];
+        if (c) {
+            if (SCATTER) { base[t] = atomicAdd(tile_cursor + t, c); hist[t] = 0u; }
+            else atomicAdd(tile_count + t, c);
+        }
+    }
+    if (!SCATTER) return;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < GSR_MS_ITEMS; ++u) {
+        if (rd[u].w) {
+            const int i = i0 + u * 1024 + threadIdx.x;
+            const int minx = rd[u].x & 0xffff, miny = rd[u].x >> 16, maxx = rd[u].y & 0xffff, maxy = rd[u].y >> 16;
+            const unsigned long long key = ((unsigned long long)rd[u].z << 32) | (uint32_t)i;
+            for (int ty = miny; ty < maxy; ++ty)
+                for (int tx = minx; tx < maxx; ++tx) {
+                    const int t = ty * gx + tx;
+                    const uint32_t pos = base[t] + atomicAdd(&hist[t], 1u);
+                    if (pos < max_pairs) keys[pos] = key;
+                }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // In-smem LSD radix sort of n <= NT*ITEMS 64-bit keys on their HIGH 32 bits (depth), followed by a
 // pass that orders runs of equal depth by the low 32 bits (Gaussian index).
 // Element order is warp-major: warp w owns rows j = 0..rows-1 of 32 consecutive elements
@@ -527,8 +581,34 @@ cudaError_t gsr_launch_scan(const GsrFwdArgs& a) {
     return cudaGetLastError();
 }
 
+static cudaError_t launch_multisplit(const GsrFwdArgs& a, const BinPtrs& b, bool scatter) {
+    const int P = a.prm.P;
+    if (P == 0) return cudaSuccess;
+    const int per = 1024 * GSR_MS_ITEMS;
+    const int smem = 2 * b.grid.ntiles * (int)sizeof(uint32_t);
+    cudaError_t e = scatter
+        ? cudaFuncSetAttribute(multisplit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+        : cudaFuncSetAttribute(multisplit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    if (scatter)
+        multisplit_kernel<true><<<(P + per - 1) / per, 1024, smem, a.stream>>>(
+            P, b.grid.gx, b.grid.ntiles, a.max_pairs, b.rectdepth, b.tile_count, b.tile_cursor, b.keys);
+    else
+        multisplit_kernel<false><<<(P + per - 1) / per, 1024, smem, a.stream>>>(
+            P, b.grid.gx, b.grid.ntiles, a.max_pairs, b.rectdepth, b.tile_count, b.tile_cursor, b.keys);
+    return cudaGetLastError();
+}
+
+// multisplit path only: the fallback path counts inside project_sh
+cudaError_t gsr_launch_count(const GsrFwdArgs& a) {
+    const BinPtrs b = bin_ptrs(a);
+    if (!gsr_use_multisplit(b.grid.ntiles)) return cudaSuccess;
+    return launch_multisplit(a, b, false);
+}
+
 cudaError_t gsr_launch_scatter(const GsrFwdArgs& a) {
     const BinPtrs b = bin_ptrs(a);
+    if (gsr_use_multisplit(b.grid.ntiles)) return launch_multisplit(a, b, true);
     if (a.prm.P > 0)
         scatter_kernel<<<(a.prm.P + 255) / 256, 256, 0, a.stream>>>(a.prm.P, b.grid.gx, b.grid.ntiles,
                                                                      a.max_pairs, b.rectdepth, b.tile_cursor,

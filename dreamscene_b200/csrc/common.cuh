@@ -60,6 +60,12 @@ enum { GSR_C_FWD_QUEUE = 0, GSR_C_BWD_QUEUE = GSR_NQUEUE };
 // Tile counters/cursors are privatised into GSR_COPIES arrays (copy = (gaussian_idx>>5) & mask):
 // same-address L2 atomics serialise at ~30 ns each, so the hottest tile bounds the kernel.
 #define GSR_COPIES 16
+// Block-multisplit binning (default when the tile grid fits in shared memory): a CTA of 1024
+// threads owns GSR_MS_ITEMS*1024 consecutive Gaussians and histograms their tile hits in smem, so
+// global atomics drop from one per (Gaussian, tile) pair to one per (CTA, touched tile).
+#define GSR_MS_ITEMS 4
+#define GSR_MS_MAX_TILES 12288   // 2 x 4 B x tiles of dynamic smem (96 KB)
+__host__ __device__ inline bool gsr_use_multisplit(int ntiles) { return ntiles <= GSR_MS_MAX_TILES; }
 
 #ifdef __CUDACC__
 // ---- 128-bit global access helpers -------------------------------------------------------
@@ -133,6 +139,7 @@ struct GsrBwdArgs {
 };
 
 cudaError_t gsr_launch_project(const GsrFwdArgs& a);
+cudaError_t gsr_launch_count(const GsrFwdArgs& a);         // multisplit path: per-tile pair counts
 cudaError_t gsr_launch_scan(const GsrFwdArgs& a);          // exclusive scan + work order + host notify
 cudaError_t gsr_launch_scatter(const GsrFwdArgs& a);       // append keys to tile lists
 cudaError_t gsr_launch_sort(const GsrFwdArgs& a);          // per-tile sort + record gather (2 kernels)

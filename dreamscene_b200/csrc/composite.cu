@@ -93,9 +93,12 @@ __device__ __forceinline__ bool cull_pass(float px, float py, uint32_t ext, floa
 // Forward keeps the tile as the unit of work: blocks that never saturate (silhouettes, thin
 // regions) must scan the whole list, and sharing each gathered 256-entry chunk between the 8
 // warps of the tile makes that scan cheap (measured: 0.145 ms vs 0.170 ms for independent warps).
-constexpr int kChunk = 256;   // list entries per pipeline stage (one per thread)
+#ifndef GSR_FWD_CHUNK
+#define GSR_FWD_CHUNK 256
+#endif
+constexpr int kChunk = GSR_FWD_CHUNK;   // list entries per pipeline stage (kChunk/256 per thread)
 struct __align__(128) SmemCta {
-    GsrRec rec[2][kChunk];   // 2 x 12 KB
+    GsrRec rec[2][kChunk];   // 2 x 12 KB at kChunk = 256
     uint32_t work;           // broadcast slot for the tile queue
 };
 

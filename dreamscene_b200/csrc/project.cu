@@ -325,10 +325,13 @@ project_sh_kernel(b200gsr_params p, const float* __restrict__ means3D,
     }
     if (!vis) return;
 
-    // tile counters first: the RED atomics overlap the colour math below
-    uint32_t* cnt = tile_count + (size_t)((i >> 5) & (GSR_COPIES - 1)) * grid.ntiles;
-    for (int ty = miny; ty < maxy; ++ty)
-        for (int tx = minx; tx < maxx; ++tx) atomicAdd(cnt + ty * grid.gx + tx, 1u);
+    // fallback binning only (tile grid too large for the smem multisplit): privatised global
+    // tile counters; the RED atomics overlap the colour math below
+    if (!gsr_use_multisplit(grid.ntiles)) {
+        uint32_t* cnt = tile_count + (size_t)((i >> 5) & (GSR_COPIES - 1)) * grid.ntiles;
+        for (int ty = miny; ty < maxy; ++ty)
+            for (int tx = minx; tx < maxx; ++tx) atomicAdd(cnt + ty * grid.gx + tx, 1u);
+    }
 
     float rgb[3];
     if (shs != nullptr) {
