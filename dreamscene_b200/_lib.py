@@ -30,7 +30,7 @@ class SavedLayout(C.Structure):
 
 class ScratchLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in ("counters", "tile_count", "tile_cursor", "rectdepth",
-                                          "dgeom", "total")]
+                                          "ms_hist", "dgeom", "total")]
 
 
 _lib = None

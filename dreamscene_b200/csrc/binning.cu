@@ -28,7 +28,7 @@ __device__ __forceinline__ int size_bucket(uint32_t n) {   // 0 = longest lists
 }
 
 __global__ void __launch_bounds__(1024)
-scan_order_kernel(int ntiles, uint32_t max_pairs, const uint32_t* __restrict__ tile_count,
+scan_order_kernel(int ntiles, int ncopies, uint32_t max_pairs, const uint32_t* __restrict__ tile_count,
                   uint32_t* __restrict__ tile_start, uint32_t* __restrict__ tile_cursor,
                   uint32_t* __restrict__ work_order, uint32_t* __restrict__ header,
                   volatile uint32_t* host_notify, uint32_t notify_seq) {
@@ -46,7 +46,7 @@ scan_order_kernel(int ntiles, uint32_t max_pairs, const uint32_t* __restrict__ t
         uint32_t v = 0;
 #pragma unroll
         for (int c = 0; c < GSR_COPIES; ++c) {
-            cnt[c] = (t < ntiles) ? tile_count[(size_t)c * ntiles + t] : 0u;
+            cnt[c] = (t < ntiles && c < ncopies) ? tile_count[(size_t)c * ntiles + t] : 0u;
             v += cnt[c];
         }
         uint32_t incl = v;
@@ -110,7 +110,8 @@ scan_order_kernel(int ntiles, uint32_t max_pairs, const uint32_t* __restrict__ t
     for (int t = tid; t < ntiles; t += 1024) {
         uint32_t v = 0;
 #pragma unroll
-        for (int c = 0; c < GSR_COPIES; ++c) v += tile_count[(size_t)c * ntiles + t];
+        for (int c = 0; c < GSR_COPIES; ++c)
+            if (c < ncopies) v += tile_count[(size_t)c * ntiles + t];
         const uint32_t pos = atomicAdd(&bucket_pos[size_bucket(v)], 1u);
         work_order[pos] = (uint32_t)t;
     }
@@ -150,54 +151,64 @@ scatter_kernel(int P, int gx, int ntiles, uint32_t max_pairs, const uint4* __res
 
 // ---------------------------------------------------------------------------------------------
 // Block multisplit (default path).  count: smem histogram of the CTA's tile hits, then ONE global
-// RED per touched tile.  scatter: same histogram again, ONE returned global atomic per touched tile
-// reserves the CTA's contiguous slice of that tile's segment, then every pair takes its slot
-// inside the slice from a shared-memory atomic.
+// RED per touched tile; the histogram is kept in global memory.  scatter: re-reads it, ONE returned
+// global atomic per touched tile reserves the CTA's contiguous slice of that tile's segment, then
+// every pair takes its slot inside the slice from a shared-memory atomic.
 // ---------------------------------------------------------------------------------------------
 template <bool SCATTER>
 __global__ void __launch_bounds__(1024)
 multisplit_kernel(int P, int gx, int ntiles, uint32_t max_pairs, const uint4* __restrict__ rectdepth,
                   uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_cursor,
-                  unsigned long long* __restrict__ keys) {
+                  uint32_t* __restrict__ block_hist, unsigned long long* __restrict__ keys) {
     extern __shared__ uint32_t ms_smem[];
     uint32_t* hist = ms_smem;            // [ntiles] counts, later in-slice cursors
     uint32_t* base = ms_smem + ntiles;   // [ntiles] start of this CTA's slice (SCATTER only)
-    for (int t = threadIdx.x; t < ntiles; t += 1024) hist[t] = 0u;
-    __syncthreads();
     const int i0 = blockIdx.x * (1024 * GSR_MS_ITEMS);
+    uint32_t* my_hist = block_hist + (size_t)blockIdx.x * ntiles;   // written by count, re-read by scatter
     uint4 rd[GSR_MS_ITEMS];
 #pragma unroll
     for (int u = 0; u < GSR_MS_ITEMS; ++u) {
         const int i = i0 + u * 1024 + threadIdx.x;
         rd[u] = (i < P) ? __ldg(rectdepth + i) : make_uint4(0u, 0u, 0u, 0u);
-        if (rd[u].w) {
-            const int minx = rd[u].x & 0xffff, miny = rd[u].x >> 16, maxx = rd[u].y & 0xffff, maxy = rd[u].y >> 16;
-            for (int ty = miny; ty < maxy; ++ty)
-                for (int tx = minx; tx < maxx; ++tx) atomicAdd(&hist[ty * gx + tx], 1u);
-        }
     }
-    __syncthreads();
-    for (int t = threadIdx.x; t < ntiles; t += 1024) {
-        const uint32_t c = hist[t];
-        if (c) {
-            if (SCATTER) { base[t] = atomicAdd(tile_cursor + t, c); hist[t] = 0u; }
-            else atomicAdd(tile_count + t, c);
-        }
-    }
-    if (!SCATTER) return;
-    __syncthreads();
+    if constexpr (!SCATTER) {
+        for (int t = threadIdx.x; t < ntiles; t += 1024) hist[t] = 0u;
+        __syncthreads();
 #pragma unroll
-    for (int u = 0; u < GSR_MS_ITEMS; ++u) {
-        if (rd[u].w) {
-            const int i = i0 + u * 1024 + threadIdx.x;
-            const int minx = rd[u].x & 0xffff, miny = rd[u].x >> 16, maxx = rd[u].y & 0xffff, maxy = rd[u].y >> 16;
-            const unsigned long long key = ((unsigned long long)rd[u].z << 32) | (uint32_t)i;
-            for (int ty = miny; ty < maxy; ++ty)
-                for (int tx = minx; tx < maxx; ++tx) {
-                    const int t = ty * gx + tx;
-                    const uint32_t pos = base[t] + atomicAdd(&hist[t], 1u);
-                    if (pos < max_pairs) keys[pos] = key;
-                }
+        for (int u = 0; u < GSR_MS_ITEMS; ++u) {
+            if (rd[u].w) {
+                const int minx = rd[u].x & 0xffff, miny = rd[u].x >> 16, maxx = rd[u].y & 0xffff, maxy = rd[u].y >> 16;
+                for (int ty = miny; ty < maxy; ++ty)
+                    for (int tx = minx; tx < maxx; ++tx) atomicAdd(&hist[ty * gx + tx], 1u);
+            }
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < ntiles; t += 1024) {
+            const uint32_t c = hist[t];
+            my_hist[t] = c;
+            if (c) atomicAdd(tile_count + t, c);
+        }
+    } else {
+        // reserve this CTA's slice of every touched tile, zero the in-slice cursors
+        for (int t = threadIdx.x; t < ntiles; t += 1024) {
+            const uint32_t c = my_hist[t];
+            hist[t] = 0u;
+            if (c) base[t] = atomicAdd(tile_cursor + t, c);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < GSR_MS_ITEMS; ++u) {
+            if (rd[u].w) {
+                const int i = i0 + u * 1024 + threadIdx.x;
+                const int minx = rd[u].x & 0xffff, miny = rd[u].x >> 16, maxx = rd[u].y & 0xffff, maxy = rd[u].y >> 16;
+                const unsigned long long key = ((unsigned long long)rd[u].z << 32) | (uint32_t)i;
+                for (int ty = miny; ty < maxy; ++ty)
+                    for (int tx = minx; tx < maxx; ++tx) {
+                        const int t = ty * gx + tx;
+                        const uint32_t pos = base[t] + atomicAdd(&hist[t], 1u);
+                        if (pos < max_pairs) keys[pos] = key;
+                    }
+            }
         }
     }
 }
@@ -575,7 +586,8 @@ BinPtrs bin_ptrs(const GsrFwdArgs& a) {
 
 cudaError_t gsr_launch_scan(const GsrFwdArgs& a) {
     const BinPtrs b = bin_ptrs(a);
-    scan_order_kernel<<<1, 1024, 0, a.stream>>>(b.grid.ntiles, a.max_pairs, b.tile_count, b.tile_start,
+    scan_order_kernel<<<1, 1024, 0, a.stream>>>(b.grid.ntiles, gsr_use_multisplit(b.grid.ntiles) ? 1 : GSR_COPIES,
+                                                 a.max_pairs, b.tile_count, b.tile_start,
                                                  b.tile_cursor, b.work_order, b.header, a.host_notify,
                                                  a.notify_seq);
     return cudaGetLastError();
@@ -592,10 +604,12 @@ static cudaError_t launch_multisplit(const GsrFwdArgs& a, const BinPtrs& b, bool
     if (e != cudaSuccess) return e;
     if (scatter)
         multisplit_kernel<true><<<(P + per - 1) / per, 1024, smem, a.stream>>>(
-            P, b.grid.gx, b.grid.ntiles, a.max_pairs, b.rectdepth, b.tile_count, b.tile_cursor, b.keys);
+            P, b.grid.gx, b.grid.ntiles, a.max_pairs, b.rectdepth, b.tile_count, b.tile_cursor,
+            reinterpret_cast<uint32_t*>(a.scratch + a.sl.ms_hist), b.keys);
     else
         multisplit_kernel<false><<<(P + per - 1) / per, 1024, smem, a.stream>>>(
-            P, b.grid.gx, b.grid.ntiles, a.max_pairs, b.rectdepth, b.tile_count, b.tile_cursor, b.keys);
+            P, b.grid.gx, b.grid.ntiles, a.max_pairs, b.rectdepth, b.tile_count, b.tile_cursor,
+            reinterpret_cast<uint32_t*>(a.scratch + a.sl.ms_hist), b.keys);
     return cudaGetLastError();
 }
 
