@@ -42,6 +42,26 @@ void prof_mark_bwd(int k, cudaStream_t s) {
         cudaEventRecord(g_prof.bwd[g_prof.nbwd * kBwdEvents + k], s);
 }
 
+// ---- forked stream (per device, created lazily, never destroyed): lets the two tile-sort size
+// classes run concurrently.  Process-wide state, used from one host thread at a time.
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+SideStream g_side[64];
+
+SideStream* side_stream() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    SideStream& s = g_side[dev];
+    if (!s.stream) {
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) { s.stream = nullptr; return nullptr; }
+    }
+    return &s;
+}
+
 int validate_inputs(const b200gsr_params* p, const float* means3D, const float* shs,
                     const float* colors, const float* opac, const float* scales,
                     const float* rots, const float* cov3d) {
@@ -151,7 +171,11 @@ int b200gsr_forward(const b200gsr_params* prm, const float* means3D, const float
     prof_mark_fwd(2, a.stream);
     if ((rc = check_cuda(gsr_launch_scatter(a), "scatter"))) return rc;
     prof_mark_fwd(3, a.stream);
-    if ((rc = check_cuda(gsr_launch_sort(a), "tile_sort"))) return rc;
+    {
+        SideStream* side = side_stream();
+        if ((rc = check_cuda(gsr_launch_sort(a, side ? side->stream : nullptr, side ? side->fork : nullptr,
+                                             side ? side->join : nullptr), "tile_sort"))) return rc;
+    }
     prof_mark_fwd(4, a.stream);
     if ((rc = check_cuda(gsr_launch_composite_fwd(a), "composite_fwd"))) return rc;
     prof_mark_fwd(5, a.stream);

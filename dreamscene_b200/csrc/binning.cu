@@ -630,7 +630,9 @@ cudaError_t gsr_launch_scatter(const GsrFwdArgs& a) {
     return cudaGetLastError();
 }
 
-cudaError_t gsr_launch_sort(const GsrFwdArgs& a) {
+// The two size classes touch disjoint tiles, so when the caller provides a forked stream the
+// small-tile kernel runs there concurrently with the big-tile kernel (joined before returning).
+cudaError_t gsr_launch_sort(const GsrFwdArgs& a, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join) {
     const BinPtrs b = bin_ptrs(a);
     const int big_smem = (int)sizeof(SortSmemBig), small_smem = (int)sizeof(SortSmemSmall);
     cudaError_t e = cudaFuncSetAttribute(sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem);
@@ -645,7 +647,17 @@ cudaError_t gsr_launch_sort(const GsrFwdArgs& a) {
     }
     const int small_grid = min(b.grid.ntiles, nsm * 4);
     const int big_grid = min(b.grid.ntiles, nsm);
+    cudaStream_t s_small = a.stream;
+    if (side != nullptr) {
+        if ((e = cudaEventRecord(fork, a.stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(side, fork, 0)) != cudaSuccess) return e;
+        s_small = side;
+    }
     sort_big_kernel<<<big_grid, 1024, big_smem, a.stream>>>(b.header, b.work_order, b.tile_start, b.keys);
-    sort_small_kernel<<<small_grid, 256, small_smem, a.stream>>>(b.header, b.work_order, b.tile_start, b.keys);
+    sort_small_kernel<<<small_grid, 256, small_smem, s_small>>>(b.header, b.work_order, b.tile_start, b.keys);
+    if (side != nullptr) {
+        if ((e = cudaEventRecord(join, side)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(a.stream, join, 0)) != cudaSuccess) return e;
+    }
     return cudaGetLastError();
 }

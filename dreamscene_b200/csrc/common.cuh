@@ -142,7 +142,7 @@ cudaError_t gsr_launch_project(const GsrFwdArgs& a);
 cudaError_t gsr_launch_count(const GsrFwdArgs& a);         // multisplit path: per-tile pair counts
 cudaError_t gsr_launch_scan(const GsrFwdArgs& a);          // exclusive scan + work order + host notify
 cudaError_t gsr_launch_scatter(const GsrFwdArgs& a);       // append keys to tile lists
-cudaError_t gsr_launch_sort(const GsrFwdArgs& a);          // per-tile sort + record gather (2 kernels)
+cudaError_t gsr_launch_sort(const GsrFwdArgs& a, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join);   // per-tile sort (2 kernels, concurrent when `side` is given)
 cudaError_t gsr_launch_composite_fwd(const GsrFwdArgs& a);
 cudaError_t gsr_launch_composite_bwd(const GsrBwdArgs& a);
 cudaError_t gsr_launch_project_bwd(const GsrBwdArgs& a);
