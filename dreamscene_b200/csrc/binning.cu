@@ -3,10 +3,14 @@
 // Replaces upstream's InclusiveSum + duplicateWithKeys + global 64-bit cub::DeviceRadixSort +
 // identifyTileRanges with a counting-sort by tile followed by
 // an independent in-shared-memory sort of every tile's list:
-//   project_sh        : per-tile pair counts (privatised RED atomics)             [project.cu]
-//   scan_order_kernel : exclusive scan -> tile_start[], per-copy cursors, total pair count, and
-//                       the work order (tiles bucketed by list length, longest first)
-//   scatter_kernel    : every Gaussian appends (depth_bits<<32 | idx) to each tile it touches
+//   multisplit<count> : per-tile pair counts: 4096-Gaussian CTAs histogram their tile hits in shared
+//                       memory, one global RED per (CTA, touched tile)   [large tile grids: privatised
+//                       global REDs inside project_sh instead]
+//   scan_order_kernel : exclusive scan -> tile_start[], cursors, total pair count (also written to a
+//                       mapped host word), and the work order (tiles by list length, longest first)
+//   multisplit<scatter>: every Gaussian appends (depth_bits<<32 | idx) to each tile it touches; a CTA
+//                       reserves one slice per touched tile, ranks inside it come from smem atomics
+//                       [fallback: scatter_kernel with returned global atomics]
 //                       (arrival order inside a tile is arbitrary ...)
 //   sort kernels      : ... and is then fixed by sorting each tile's keys on (depth bits, idx):
 //                       identical to a stable sort of (tile<<32 | depth bits) over pairs emitted

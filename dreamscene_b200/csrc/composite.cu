@@ -2,7 +2,7 @@
 //
 // Replaces upstream's renderCUDA forward/backward (restated
 // in oracle/splat_ref.py::composite).  B200 design:
-//   * persistent CTAs pull work from a split queue ordered longest-list-first.  FORWARD: a CTA
+//   * persistent CTAs pull work from a queue ordered longest-list-first.  FORWARD: a CTA
 //     (8 warps x (8x4)-pixel blocks) takes a whole 16x16 tile and shares every gathered chunk;
 //     BACKWARD: every warp is an independent worker on one 8x4 block (lists are truncated at the
 //     block's own last contributor, so there is no long scan to share and no CTA barrier at all);
@@ -24,10 +24,10 @@
 
 namespace {
 
-// Work item = one warp's 8x4 pixel block of one non-empty tile (8 items per tile, queue ordered
-// longest list first).  Every warp is an independent worker with a private ring of kSlots
-// sub-chunks (32 records = one per lane): no CTA-wide barrier exists anywhere in these kernels.
-constexpr int kWarps = 8;      // warps per CTA (just a container; they never synchronise)
+// BACKWARD work item = one warp's 8x4 pixel block of one non-empty tile (8 items per tile, queue
+// ordered longest list first).  Every warp is an independent worker with a private ring of kSlots
+// sub-chunks (32 records = one per lane): the backward kernel contains no CTA-wide barrier.
+constexpr int kWarps = 8;      // warps per CTA (in the backward kernel just a container)
 // kSlots (template parameter of the backward kernel) = sub-chunks in the ring per warp
 // (kSlots-1 being gathered + 1 being blended); 1.5 KB per slot and warp.
 template <int kSlots>
