@@ -161,8 +161,14 @@ int b200gsr_forward(const b200gsr_params* prm, const float* means3D, const float
     a.host_notify = host_notify; a.notify_seq = notify_seq;
     a.stream = static_cast<cudaStream_t>(stream);
 
-    // counters + tile_count are contiguous at the start of scratch: one memset
-    if ((rc = check_cuda(cudaMemsetAsync(a.scratch, 0, a.sl.tile_cursor, a.stream), "memset"))) return rc;
+    // counters + tile_count are contiguous at the start of scratch: one memset (the multisplit
+    // path only uses the first of the GSR_COPIES counter arrays)
+    {
+        const GsrTileGrid tg = gsr_grid(prm->image_height, prm->image_width);
+        const size_t nbytes = gsr_use_multisplit(tg.ntiles) ? a.sl.tile_count + (size_t)tg.ntiles * sizeof(uint32_t)
+                                                            : a.sl.tile_cursor;
+        if ((rc = check_cuda(cudaMemsetAsync(a.scratch, 0, nbytes, a.stream), "memset"))) return rc;
+    }
     prof_mark_fwd(0, a.stream);
     if ((rc = check_cuda(gsr_launch_project(a), "project_sh"))) return rc;
     if ((rc = check_cuda(gsr_launch_count(a), "tile_count"))) return rc;

@@ -121,6 +121,102 @@ scan_order_kernel(int ntiles, int ncopies, uint32_t max_pairs, const uint32_t* _
     }
 }
 
+// Single-pass variant for the multisplit path (one counter copy, ntiles <= 1024*kScanItems): every
+// thread owns kScanItems consecutive tiles in registers, so there are two barriers in total and
+// the counts are never re-read.
+constexpr int kScanItems = GSR_MS_MAX_TILES / 1024;   // 12
+
+__global__ void __launch_bounds__(1024)
+scan_order_fast_kernel(int ntiles, uint32_t max_pairs, const uint32_t* __restrict__ tile_count,
+                       uint32_t* __restrict__ tile_start, uint32_t* __restrict__ tile_cursor,
+                       uint32_t* __restrict__ work_order, uint32_t* __restrict__ header,
+                       volatile uint32_t* host_notify, uint32_t notify_seq) {
+    extern __shared__ uint32_t cnt_s[];                  // [ntiles] copy of the counts for the last pass
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t bucket_cnt[33];
+    __shared__ uint32_t bucket_pos[33];
+    __shared__ uint32_t total_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int per = (ntiles + 1023) / 1024;             // tiles per thread (<= kScanItems)
+    if (tid < 33) bucket_cnt[tid] = 0;
+    uint32_t v[kScanItems], sum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        const int t = tid * per + k;
+        v[k] = (k < per && t < ntiles) ? __ldg(tile_count + t) : 0u;
+        if (k < per && t < ntiles) cnt_s[t] = v[k];
+        sum += v[k];
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t w = warp_sums[lane];
+        uint32_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += n;
+        }
+        warp_sums[lane] = wi - w;   // exclusive
+        if (lane == 31) total_s = wi;
+    }
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        const int t = tid * per + k;
+        if (k < per && t < ntiles) atomicAdd(&bucket_cnt[size_bucket(v[k])], 1u);
+    }
+    __syncthreads();
+    uint32_t run = warp_sums[wid] + incl - sum;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        const int t = tid * per + k;
+        if (k < per && t < ntiles) { tile_start[t] = run; tile_cursor[t] = run; }
+        run += v[k];
+    }
+    if (wid == 0) {   // exclusive prefix over the 33 length buckets (bucket 32 = empty tiles, handled by lane 0)
+        const uint32_t c = bucket_cnt[lane];
+        uint32_t ci = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, ci, o);
+            if (lane >= o) ci += n;
+        }
+        bucket_pos[lane] = ci - c;
+        const uint32_t nonempty = __shfl_sync(0xffffffffu, ci, 31);
+        const uint32_t nbig = __shfl_sync(0xffffffffu, ci, 19);   // buckets 0..19: n >= 4096
+        if (lane == 0) {
+            bucket_pos[32] = nonempty;
+            const uint32_t total = total_s;
+            tile_start[ntiles] = total;
+            header[GSR_H_NUM_PAIRS] = total;
+            header[GSR_H_MAX_PAIRS] = max_pairs;
+            header[GSR_H_NUM_TILES] = (uint32_t)ntiles;
+            header[GSR_H_OVERFLOW] = total > max_pairs ? 1u : 0u;
+            header[GSR_H_NUM_BIG] = nbig;
+            header[GSR_H_NUM_NONEMPTY] = nonempty;
+            if (host_notify != nullptr) {   // mapped pinned host memory: tell the host the pair count now
+                host_notify[1] = total;
+                host_notify[2] = total > max_pairs ? 1u : 0u;
+                host_notify[3] = (uint32_t)ntiles;
+                __threadfence_system();
+                host_notify[0] = notify_seq;
+            }
+        }
+    }
+    __syncthreads();
+    // Insertion order inside a length bucket matters: tiles are taken thread-strided (t, t+1024, ...)
+    // so that spatially adjacent tiles - which share Gaussians and would contend on the same
+    // gradient accumulators in composite_bwd - are not handed out back to back by a single thread.
+    for (int t = tid; t < ntiles; t += 1024)
+        work_order[atomicAdd(&bucket_pos[size_bucket(cnt_s[t])], 1u)] = (uint32_t)t;
+}
+
 // ---------------------------------------------------------------------------------------------
 // scatter: one Gaussian per thread appends its key to every touched tile
 // ---------------------------------------------------------------------------------------------
@@ -590,6 +686,12 @@ BinPtrs bin_ptrs(const GsrFwdArgs& a) {
 
 cudaError_t gsr_launch_scan(const GsrFwdArgs& a) {
     const BinPtrs b = bin_ptrs(a);
+    if (gsr_use_multisplit(b.grid.ntiles)) {
+        scan_order_fast_kernel<<<1, 1024, b.grid.ntiles * sizeof(uint32_t), a.stream>>>(b.grid.ntiles, a.max_pairs, b.tile_count, b.tile_start,
+                                                          b.tile_cursor, b.work_order, b.header, a.host_notify,
+                                                          a.notify_seq);
+        return cudaGetLastError();
+    }
     scan_order_kernel<<<1, 1024, 0, a.stream>>>(b.grid.ntiles, gsr_use_multisplit(b.grid.ntiles) ? 1 : GSR_COPIES,
                                                  a.max_pairs, b.tile_count, b.tile_start,
                                                  b.tile_cursor, b.work_order, b.header, a.host_notify,
