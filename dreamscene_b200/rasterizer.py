@@ -163,10 +163,11 @@ def _forward_impl(rs, means3D, shs, colors, opac, scales, rots, cov3d):
         pairs = int(n[1]) & 0xFFFFFFFF
         ws.last_pairs = pairs
         if pairs <= cap:
-            # keep ~25% head-room over the recent need, but never shrink below what just worked
-            ws.capacity = max(_round_cap(int(pairs * 1.25)), _MIN_CAPACITY)
+            # high-water mark with 25% head-room: the capacity only costs 8 B per pair in `saved`, and
+            # views of one training step differ a lot in pair count (random cameras), so never shrink
+            ws.capacity = max(ws.capacity, _round_cap(int(pairs * 1.25)), _MIN_CAPACITY)
             break
-        cap = ws.capacity = _round_cap(int(pairs * 1.25))   # overflow: re-issue with enough room
+        cap = ws.capacity = _round_cap(int(pairs * 1.5))   # overflow: re-issue with enough room
         if score is not None:
             score.zero_()
     st = _State()
