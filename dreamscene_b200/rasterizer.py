@@ -100,10 +100,10 @@ def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return t
 
 
-def _make_params(rs: GaussianRasterizationSettings, P: int, M: int, keep: list) -> _lib.Params:
-    dev = rs.viewmatrix.device
-    bg = _f32c(rs.bg.to(dev)); vm = _f32c(rs.viewmatrix); pm = _f32c(rs.projmatrix.to(dev))
-    cp = _f32c(rs.campos.to(dev))
+def _make_params(rs: GaussianRasterizationSettings, P: int, M: int, keep: list, dev) -> _lib.Params:
+    # the per-view constants live on the Gaussians' device (upstream requires CUDA tensors here too)
+    bg = _f32c(rs.bg.detach().to(dev)); vm = _f32c(rs.viewmatrix.detach().to(dev))
+    pm = _f32c(rs.projmatrix.detach().to(dev)); cp = _f32c(rs.campos.detach().to(dev))
     keep.extend([bg, vm, pm, cp])
     return _lib.Params(P, M, int(rs.sh_degree), int(rs.image_height), int(rs.image_width),
                        float(rs.tanfovx), float(rs.tanfovy), float(rs.scale_modifier),
@@ -126,7 +126,7 @@ def _forward_impl(rs, means3D, shs, colors, opac, scales, rots, cov3d):
     M = int(shs.shape[1]) if shs is not None else 0
     H, W = int(rs.image_height), int(rs.image_width)
     keep: list = []
-    prm = _make_params(rs, P, M, keep)
+    prm = _make_params(rs, P, M, keep, dev)
     color = torch.empty(3, H, W, dtype=torch.float32, device=dev)
     depth_alpha = torch.empty(2, H, W, dtype=torch.float32, device=dev)
     radii = torch.empty(P, dtype=torch.int32, device=dev)
@@ -245,7 +245,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             if torch.cuda.current_device() != dev.index:
                 torch.cuda.set_device(dev)
             keep: list = []
-            prm = _make_params(rs, P, M, keep)
+            prm = _make_params(rs, P, M, keep, dev)
             ws = _workspace(dev)
             sl = _lib.scratch_layout(P, H, W, st.capacity)
             scratch = ws.ensure_scratch(sl.total)
