@@ -687,6 +687,10 @@ BinPtrs bin_ptrs(const GsrFwdArgs& a) {
 cudaError_t gsr_launch_scan(const GsrFwdArgs& a) {
     const BinPtrs b = bin_ptrs(a);
     if (gsr_use_multisplit(b.grid.ntiles)) {
+        // static + dynamic shared memory can exceed the 48 KB default at the top of the range
+        cudaError_t e = cudaFuncSetAttribute(scan_order_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             GSR_MS_MAX_TILES * (int)sizeof(uint32_t));
+        if (e != cudaSuccess) return e;
         scan_order_fast_kernel<<<1, 1024, b.grid.ntiles * sizeof(uint32_t), a.stream>>>(b.grid.ntiles, a.max_pairs, b.tile_count, b.tile_start,
                                                           b.tile_cursor, b.work_order, b.header, a.host_notify,
                                                           a.notify_seq);

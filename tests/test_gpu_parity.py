@@ -320,6 +320,17 @@ def test_large_tile_grid_uses_the_global_atomic_binning_fallback():
     check_images(cu, ref)
 
 
+def test_tile_grid_at_the_multisplit_limit():
+    """2048x1536 = exactly 12288 tiles: the largest grid on the shared-memory binning path."""
+    H, W = 1536, 2048
+    sc, cam, deg = U.make_inputs(600, H, W, seed=43, exact_knn=False, scale_mul=0.5)
+    ref = run_oracle(sc, cam, deg)
+    cu = run_cuda(sc, cam, deg)
+    np.testing.assert_array_equal(cu["radii"].cpu().numpy(), ref["radii"].numpy())
+    check_lists(sc, cam, ref)
+    check_images(cu, ref)
+
+
 def test_api_errors_match_reference_messages():
     from dreamscene_b200 import GaussianRasterizer
     sc, cam, deg = U.make_inputs(16, 32, 32)
