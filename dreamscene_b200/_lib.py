@@ -41,9 +41,18 @@ def load():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise RuntimeError(
-            f"{LIB_PATH} is missing. Build it with `python -m dreamscene_b200._build` "
-            "(needs nvcc; sm_100a only). There is no CPU fallback.")
+        # Not a fallback: the only thing ever attempted is compiling the same sm_100a sources in-tree.
+        err = None
+        if "B200GSR_LIB" not in os.environ and not os.environ.get("B200GSR_NO_AUTOBUILD"):
+            try:
+                from . import _build
+                _build.build()
+            except Exception as e:   # noqa: BLE001 - reported below
+                err = e
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing and could not be built ({err}). Build it with "
+                "`python -m dreamscene_b200._build` (needs nvcc; sm_100a only). There is no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
     vp, sz, u64, u32, i32 = C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_int32
     lib.b200gsr_version.restype = C.c_int
