@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from dreamscene_b200 import GaussianRasterizationSettings, GaussianRasterizer, _lib, cameras  # noqa: E402
+from dreamscene_b200 import GaussianRasterizationSettings, GaussianRasterizer, cameras  # noqa: E402
 
 SH_C0 = 0.28209479177387814
 

@@ -60,7 +60,7 @@ def _cpu_zeros(*a, **k):
 torch.zeros = _cpu_zeros
 torch.Tensor.cuda = lambda self, *a, **k: self
 
-from utils.sh_utils import eval_sh, RGB2SH, SH2RGB            # noqa: E402
+from utils.sh_utils import eval_sh, RGB2SH                    # noqa: E402
 from utils.graphics_utils import fov2focal, focal2fov          # noqa: E402
 from utils.cam_utils import circle_poses, RCamera              # noqa: E402
 import gs_renderer                                              # noqa: E402

@@ -1,6 +1,5 @@
 """Shared helpers for the parity tests: scene construction, oracle runs, decoding the CUDA
 library's saved buffers."""
-import math
 
 import numpy as np
 import torch

@@ -1,4 +1,4 @@
-import os, time, torch, torch.distributed as dist
+import os, torch, torch.distributed as dist
 rank=int(os.environ["RANK"]); world=int(os.environ["WORLD_SIZE"]); local=int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local); dev=torch.device("cuda",local)
 dist.init_process_group("nccl", device_id=dev)
