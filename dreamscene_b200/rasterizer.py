@@ -175,6 +175,19 @@ def _forward_impl(rs, means3D, shs, colors, opac, scales, rots, cov3d):
     return color, radii, depth_alpha, score, st
 
 
+def grad_sections(P: int, n_col: int, has_sr: bool):
+    """Offsets (in floats) of the parameter-gradient sections inside the flat buffer that backward
+    fills and (under view sharding) all-reduces: means3D[P,3], opac[P,1], col[P,n_col], then
+    scales[P,3]+rots[P,4] or cov[P,6].  Every section starts on a 256-byte boundary because the
+    kernels use 16-byte vector stores.  Returns (offsets dict, total floats)."""
+    widths = [("means3D", 3), ("opac", 1), ("col", n_col)] + ([("scales", 3), ("rots", 4)] if has_sr else [("cov", 6)])
+    offs, o = {}, 0
+    for name, wdt in widths:
+        offs[name] = o
+        o += (P * wdt + 63) // 64 * 64
+    return offs, o
+
+
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
@@ -218,12 +231,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         # one flat buffer for every parameter gradient: a single NCCL all-reduce when views are
         # sharded across ranks (dreamscene_b200.parallel), and one allocation otherwise
         n_col = 3 * M if has_sh else 3
-        widths = [("means3D", 3), ("opac", 1), ("col", n_col)] + ([("scales", 3), ("rots", 4)] if has_sr else [("cov", 6)])
-        # every section starts on a 256-byte boundary (the kernels use 16-byte vector stores)
-        offs, o = {}, 0
-        for name, wdt in widths:
-            offs[name] = o
-            o += (P * wdt + 63) // 64 * 64
+        offs, o = grad_sections(P, n_col, has_sr)
         flat = torch.empty(max(o, 1), dtype=torch.float32, device=dev)
         sec = lambda name, wdt: flat[offs[name]:offs[name] + P * wdt]
         d_means3D = sec("means3D", 3).view(P, 3)

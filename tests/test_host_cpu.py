@@ -76,3 +76,17 @@ def test_product_never_imports_the_oracle():
                 if f.endswith(".py"):
                     src = open(os.path.join(dp, f)).read()
                     assert "oracle" not in src.replace("no oracle", ""), os.path.join(dp, f)
+
+
+def test_gradient_sections_are_256_byte_aligned_for_any_point_count():
+    from dreamscene_b200.rasterizer import grad_sections
+    for P in (0, 1, 2, 3, 7, 1001, 1_000_000):
+        for n_col, has_sr in ((48, True), (12, True), (3, False), (27, True)):
+            offs, total = grad_sections(P, n_col, has_sr)
+            widths = dict(means3D=3, opac=1, col=n_col, scales=3, rots=4, cov=6)
+            names = list(offs)
+            assert names[:3] == ["means3D", "opac", "col"] and (("rots" in offs) == has_sr) and (("cov" in offs) != has_sr)
+            for a, b in zip(names, names[1:] + [None]):
+                assert offs[a] % 64 == 0                               # 64 floats = 256 bytes
+                end = offs[b] if b else total
+                assert end - offs[a] >= P * widths[a]                  # sections never overlap
