@@ -21,7 +21,8 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from dreamscene_b200 import GaussianRasterizationSettings, GaussianRasterizer, cameras  # noqa: E402
+from dreamscene_b200 import GaussianRasterizationSettings, GaussianRasterizer  # noqa: E402
+from harness import cameras  # noqa: E402
 
 SH_C0 = 0.28209479177387814
 
@@ -135,7 +136,7 @@ def main():
             times.append(dt)
             ras_fwd.append(sum(o["ev"][0].elapsed_time(o["ev"][1]) for o in outs))
             vis.append(float(np.mean([(o["radii"] > 0).float().mean().item() for o in outs])))
-            pairs.append(R._workspace(dev).last_pairs)
+            pairs.append(R.last_pair_count(dev))
     finite = all(torch.isfinite(p.grad).all().item() for p in params)
     print(json.dumps({"config": "cfg5_scene_step (re-enactment)", "P": P, "views": a.views, "size": a.size,
                       "M": 4, "sh_degree": 1, "step_ms": 1e3 * float(np.median(times)),

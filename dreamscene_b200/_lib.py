@@ -25,15 +25,17 @@ class Params(C.Structure):
 
 class SavedLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in ("header", "tile_start", "work_order", "n_contrib",
-                                          "keys", "geom", "total")]
+                                          "keys", "geom", "dgeom", "total")]
 
 
 class ScratchLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in ("counters", "tile_count", "tile_cursor", "rectdepth",
-                                          "ms_hist", "dgeom", "total")]
+                                          "ms_hist", "total")]
 
 
 _lib = None
+ABI_VERSION = 2
+FWD_NO_BACKWARD = 1
 
 
 def load():
@@ -57,10 +59,10 @@ def load():
     vp, sz, u64, u32, i32 = C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_int32
     lib.b200gsr_version.restype = C.c_int
     lib.b200gsr_last_error.restype = C.c_char_p
-    lib.b200gsr_saved_layout_query.argtypes = [i32, i32, i32, u64, C.POINTER(SavedLayout)]
+    lib.b200gsr_saved_layout_query.argtypes = [i32, i32, i32, u64, i32, C.POINTER(SavedLayout)]
     lib.b200gsr_scratch_layout_query.argtypes = [i32, i32, i32, u64, C.POINTER(ScratchLayout)]
     lib.b200gsr_forward.argtypes = [C.POINTER(Params)] + [vp] * 7 + [vp] * 4 + \
-        [vp, sz, vp, sz, u64, vp, u32, vp]
+        [vp, sz, vp, sz, u64, u32, vp, u32, vp]
     lib.b200gsr_backward.argtypes = [C.POINTER(Params)] + [vp] * 7 + [vp] * 4 + \
         [vp, sz, vp, sz, u64] + [vp] * 8 + [vp]
     lib.b200gsr_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]
@@ -76,6 +78,9 @@ def load():
     for f in ("b200gsr_saved_layout_query", "b200gsr_scratch_layout_query", "b200gsr_forward",
               "b200gsr_backward", "b200gsr_mark_visible"):
         getattr(lib, f).restype = C.c_int
+    if lib.b200gsr_version() != ABI_VERSION:
+        raise RuntimeError(f"{LIB_PATH} has ABI version {lib.b200gsr_version()}, this package needs "
+                           f"{ABI_VERSION}: rebuild with `python -m dreamscene_b200._build --force`")
     _lib = lib
     return lib
 
@@ -84,9 +89,9 @@ def last_error() -> str:
     return load().b200gsr_last_error().decode("utf-8", "replace")
 
 
-def saved_layout(P: int, H: int, W: int, max_pairs: int) -> SavedLayout:
+def saved_layout(P: int, H: int, W: int, max_pairs: int, with_backward: bool = True) -> SavedLayout:
     out = SavedLayout()
-    rc = load().b200gsr_saved_layout_query(P, H, W, max_pairs, C.byref(out))
+    rc = load().b200gsr_saved_layout_query(P, H, W, max_pairs, int(bool(with_backward)), C.byref(out))
     if rc:
         raise RuntimeError(f"b200gsr_saved_layout_query failed ({rc}): {last_error()}")
     return out

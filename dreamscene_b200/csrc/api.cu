@@ -4,6 +4,16 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+
+#ifndef B200GSR_NO_NVTX
+#include <nvtx3/nvToolsExt.h>   // header-only; a no-op unless a profiler is attached
+#define GSR_RANGE_PUSH(name) nvtxRangePushA(name)
+#define GSR_RANGE_POP() nvtxRangePop()
+#else
+#define GSR_RANGE_PUSH(name) ((void)0)
+#define GSR_RANGE_POP() ((void)0)
+#endif
 
 namespace {
 
@@ -42,23 +52,41 @@ void prof_mark_bwd(int k, cudaStream_t s) {
         cudaEventRecord(g_prof.bwd[g_prof.nbwd * kBwdEvents + k], s);
 }
 
-// ---- forked stream (per device, created lazily, never destroyed): lets the two tile-sort size
-// classes run concurrently.  Process-wide state, used from one host thread at a time.
-struct SideStream {
+// ---- per-device state, created lazily under a mutex and never destroyed: SM count + a forked
+// stream that lets the two tile-sort size classes run concurrently.
+struct DeviceState {
+    bool ready = false;
+    int num_sms = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
 };
-SideStream g_side[64];
+DeviceState g_dev[64];
+std::mutex g_dev_mutex;
 
-SideStream* side_stream() {
+// Returns nullptr only if the device ordinal is out of range or CUDA itself fails.
+DeviceState* device_state() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    SideStream& s = g_side[dev];
-    if (!s.stream) {
-        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) { s.stream = nullptr; return nullptr; }
+    DeviceState& s = g_dev[dev];
+    if (s.ready) return &s;                       // written once under the mutex
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    if (s.ready) return &s;
+    int nsm = 148;
+    if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && nsm > 0) s.num_sms = nsm;
+    // the side stream is optional: without it the two sort kernels simply run back to back
+    cudaStream_t st = nullptr;
+    cudaEvent_t ef = nullptr, ej = nullptr;
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess &&
+        cudaEventCreateWithFlags(&ef, cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags(&ej, cudaEventDisableTiming) == cudaSuccess) {
+        s.stream = st; s.fork = ef; s.join = ej;
+    } else {
+        if (ef) cudaEventDestroy(ef);
+        if (ej) cudaEventDestroy(ej);
+        if (st) cudaStreamDestroy(st);
+        cudaGetLastError();   // clear the non-sticky creation error
     }
+    s.ready = true;
     return &s;
 }
 
@@ -100,17 +128,18 @@ int b200gsr_version(void) { return B200GSR_VERSION; }
 const char* b200gsr_last_error(void) { return g_err; }
 
 int b200gsr_saved_layout_query(int32_t P, int32_t H, int32_t W, uint64_t max_pairs,
-                               b200gsr_saved_layout* out) {
+                               int32_t with_backward, b200gsr_saved_layout* out) {
     if (!out || P < 0 || H < 0 || W < 0) return fail(B200GSR_ERR_BAD_ARG, "bad layout query");
     if (max_pairs > 0xfffffff0ull) return fail(B200GSR_ERR_UNSUPPORTED, "max_pairs must fit in 32 bits");
     const GsrTileGrid g = gsr_grid(H, W);
     size_t off = 0;
-    out->header = off;      off = align_up(off + 8 * sizeof(uint32_t));
+    out->header = off;      off = align_up(off + GSR_H_WORDS * sizeof(uint32_t));
     out->tile_start = off;  off = align_up(off + ((size_t)g.ntiles + 1) * sizeof(uint32_t));
     out->work_order = off;  off = align_up(off + (size_t)g.ntiles * sizeof(uint32_t));
     out->n_contrib = off;   off = align_up(off + (size_t)H * W * sizeof(uint32_t));
     out->keys = off;        off = align_up(off + ((size_t)max_pairs + 2) * sizeof(uint64_t));
     out->geom = off;        off = align_up(off + (size_t)P * sizeof(GsrRec));
+    out->dgeom = off;       off = align_up(off + (with_backward ? (size_t)P * 12 * sizeof(float) : 0));
     out->total = off;
     return B200GSR_OK;
 }
@@ -129,7 +158,6 @@ int b200gsr_scratch_layout_query(int32_t P, int32_t H, int32_t W, uint64_t max_p
         const size_t nblk = ((size_t)P + 1024 * GSR_MS_ITEMS - 1) / (1024 * GSR_MS_ITEMS);
         out->ms_hist = off; off = align_up(off + (gsr_use_multisplit(g.ntiles) ? nblk * g.ntiles * sizeof(uint32_t) : 0));
     }
-    out->dgeom = off;       off = align_up(off + (size_t)P * 12 * sizeof(float));
     out->total = off;
     return B200GSR_OK;
 }
@@ -139,17 +167,20 @@ int b200gsr_forward(const b200gsr_params* prm, const float* means3D, const float
                     const float* rotations, const float* cov3D_precomp, float* out_color,
                     float* out_depth_alpha, int32_t* radii, float* score, void* scratch,
                     size_t scratch_bytes, void* saved, size_t saved_bytes, uint64_t max_pairs,
-                    uint32_t* host_notify, uint32_t notify_seq, void* stream) {
+                    uint32_t flags, uint32_t* host_notify, uint32_t notify_seq, void* stream) {
     int rc = validate_inputs(prm, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp);
     if (rc) return rc;
     if (!out_color || !out_depth_alpha || (prm->P > 0 && !radii) || !scratch || !saved)
         return fail(B200GSR_ERR_BAD_ARG, "null output/workspace pointer");
     if (prm->score_flag && prm->P > 0 && !score)
         return fail(B200GSR_ERR_BAD_ARG, "score_flag set but score buffer is null");
+    DeviceState* ds = device_state();
+    if (!ds) return fail(B200GSR_ERR_CUDA, "cannot query the current CUDA device");
     GsrFwdArgs a;
     a.prm = *prm;
+    const int with_bwd = (flags & B200GSR_FWD_NO_BACKWARD) ? 0 : 1;
     if ((rc = b200gsr_scratch_layout_query(prm->P, prm->image_height, prm->image_width, max_pairs, &a.sl))) return rc;
-    if ((rc = b200gsr_saved_layout_query(prm->P, prm->image_height, prm->image_width, max_pairs, &a.vl))) return rc;
+    if ((rc = b200gsr_saved_layout_query(prm->P, prm->image_height, prm->image_width, max_pairs, with_bwd, &a.vl))) return rc;
     if (scratch_bytes < a.sl.total || saved_bytes < a.vl.total)
         return fail(B200GSR_ERR_WORKSPACE, "workspace too small: scratch %zu < %zu or saved %zu < %zu",
                     scratch_bytes, a.sl.total, saved_bytes, a.vl.total);
@@ -159,31 +190,47 @@ int b200gsr_forward(const b200gsr_params* prm, const float* means3D, const float
     a.scratch = static_cast<uint8_t*>(scratch); a.saved = static_cast<uint8_t*>(saved);
     a.max_pairs = (uint32_t)max_pairs;
     a.host_notify = host_notify; a.notify_seq = notify_seq;
+    a.flags = flags; a.num_sms = ds->num_sms;
     a.stream = static_cast<cudaStream_t>(stream);
 
-    // counters + tile_count are contiguous at the start of scratch: one memset (the multisplit
-    // path only uses the first of the GSR_COPIES counter arrays)
+    // The queue counters and the per-tile pair counters (contiguous at the start of scratch) must be
+    // zero before the count kernel runs.  On the main path (smem multisplit binning, P > 0) the
+    // project_sh prologue zeroes them; only the large-grid fallback (project_sh itself counts with
+    // global atomics) and the P == 0 case need a memset node.
     {
         const GsrTileGrid tg = gsr_grid(prm->image_height, prm->image_width);
-        const size_t nbytes = gsr_use_multisplit(tg.ntiles) ? a.sl.tile_count + (size_t)tg.ntiles * sizeof(uint32_t)
-                                                            : a.sl.tile_cursor;
-        if ((rc = check_cuda(cudaMemsetAsync(a.scratch, 0, nbytes, a.stream), "memset"))) return rc;
+        if (!gsr_use_multisplit(tg.ntiles) || prm->P == 0) {
+            const size_t nbytes = gsr_use_multisplit(tg.ntiles) ? a.sl.tile_count + (size_t)tg.ntiles * sizeof(uint32_t)
+                                                                : a.sl.tile_cursor;
+            if ((rc = check_cuda(cudaMemsetAsync(a.scratch, 0, nbytes, a.stream), "memset"))) return rc;
+        }
     }
     prof_mark_fwd(0, a.stream);
-    if ((rc = check_cuda(gsr_launch_project(a), "project_sh"))) return rc;
-    if ((rc = check_cuda(gsr_launch_count(a), "tile_count"))) return rc;
+    GSR_RANGE_PUSH("b200gsr.project_sh+count");
+    rc = check_cuda(gsr_launch_project(a), "project_sh");
+    if (!rc) rc = check_cuda(gsr_launch_count(a), "tile_count");
+    GSR_RANGE_POP();
+    if (rc) return rc;
     prof_mark_fwd(1, a.stream);
-    if ((rc = check_cuda(gsr_launch_scan(a), "scan_order"))) return rc;
+    GSR_RANGE_PUSH("b200gsr.scan_order");
+    rc = check_cuda(gsr_launch_scan(a), "scan_order");
+    GSR_RANGE_POP();
+    if (rc) return rc;
     prof_mark_fwd(2, a.stream);
-    if ((rc = check_cuda(gsr_launch_scatter(a), "scatter"))) return rc;
+    GSR_RANGE_PUSH("b200gsr.scatter");
+    rc = check_cuda(gsr_launch_scatter(a), "scatter");
+    GSR_RANGE_POP();
+    if (rc) return rc;
     prof_mark_fwd(3, a.stream);
-    {
-        SideStream* side = side_stream();
-        if ((rc = check_cuda(gsr_launch_sort(a, side ? side->stream : nullptr, side ? side->fork : nullptr,
-                                             side ? side->join : nullptr), "tile_sort"))) return rc;
-    }
+    GSR_RANGE_PUSH("b200gsr.tile_sort");
+    rc = check_cuda(gsr_launch_sort(a, ds->stream, ds->fork, ds->join), "tile_sort");
+    GSR_RANGE_POP();
+    if (rc) return rc;
     prof_mark_fwd(4, a.stream);
-    if ((rc = check_cuda(gsr_launch_composite_fwd(a), "composite_fwd"))) return rc;
+    GSR_RANGE_PUSH("b200gsr.composite_fwd");
+    rc = check_cuda(gsr_launch_composite_fwd(a), "composite_fwd");
+    GSR_RANGE_POP();
+    if (rc) return rc;
     prof_mark_fwd(5, a.stream);
     if (g_prof.max_calls > 0 && g_prof.nfwd < g_prof.max_calls) ++g_prof.nfwd;
     return B200GSR_OK;
@@ -193,41 +240,50 @@ int b200gsr_backward(const b200gsr_params* prm, const float* means3D, const floa
                      const float* colors_precomp, const float* opacities, const float* scales,
                      const float* rotations, const float* cov3D_precomp, const int32_t* radii,
                      const float* out_depth_alpha, const float* dL_dcolor,
-                     const float* dL_ddepth_alpha, const void* saved, size_t saved_bytes,
-                     void* scratch, size_t scratch_bytes, uint64_t max_pairs, float* d_means3D,
+                     const float* dL_ddepth_alpha, void* saved, size_t saved_bytes,
+                     void* /*scratch*/, size_t /*scratch_bytes*/, uint64_t max_pairs, float* d_means3D,
                      float* d_means2D, float* d_shs, float* d_colors, float* d_opacities,
                      float* d_scales, float* d_rotations, float* d_cov3D, void* stream) {
     int rc = validate_inputs(prm, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp);
     if (rc) return rc;
     if (prm->P == 0) return B200GSR_OK;
-    if (!radii || !out_depth_alpha || !dL_dcolor || !dL_ddepth_alpha || !saved || !scratch)
+    if (!radii || !out_depth_alpha || !dL_dcolor || !dL_ddepth_alpha || !saved)
         return fail(B200GSR_ERR_BAD_ARG, "null saved-state/gradient pointer");
     if (!d_means3D || !d_means2D || !d_opacities || (shs && !d_shs) || (colors_precomp && !d_colors) ||
         (cov3D_precomp && !d_cov3D) || (!cov3D_precomp && (!d_scales || !d_rotations)))
         return fail(B200GSR_ERR_BAD_ARG, "null gradient output pointer");
+    DeviceState* ds = device_state();
+    if (!ds) return fail(B200GSR_ERR_CUDA, "cannot query the current CUDA device");
     GsrBwdArgs a;
     a.prm = *prm;
-    if ((rc = b200gsr_scratch_layout_query(prm->P, prm->image_height, prm->image_width, max_pairs, &a.sl))) return rc;
-    if ((rc = b200gsr_saved_layout_query(prm->P, prm->image_height, prm->image_width, max_pairs, &a.vl))) return rc;
-    if (scratch_bytes < a.sl.total || saved_bytes < a.vl.total)
-        return fail(B200GSR_ERR_WORKSPACE, "workspace too small: scratch %zu < %zu or saved %zu < %zu",
-                    scratch_bytes, a.sl.total, saved_bytes, a.vl.total);
+    a.sl = b200gsr_scratch_layout{};
+    if ((rc = b200gsr_saved_layout_query(prm->P, prm->image_height, prm->image_width, max_pairs, 1, &a.vl))) return rc;
+    if (saved_bytes < a.vl.total)
+        return fail(B200GSR_ERR_WORKSPACE, "saved buffer too small for backward: %zu < %zu (was the forward "
+                    "run with B200GSR_FWD_NO_BACKWARD?)", saved_bytes, a.vl.total);
     a.means3D = means3D; a.shs = shs; a.colors = colors_precomp; a.opac = opacities;
     a.scales = scales; a.rots = rotations; a.cov3d = cov3D_precomp;
     a.radii = radii; a.out_depth_alpha = out_depth_alpha;
     a.dL_dcolor = dL_dcolor; a.dL_ddepth_alpha = dL_ddepth_alpha;
-    a.saved = static_cast<const uint8_t*>(saved); a.scratch = static_cast<uint8_t*>(scratch);
+    a.saved = static_cast<uint8_t*>(saved); a.scratch = nullptr;
     a.max_pairs = (uint32_t)max_pairs;
     a.d_means3D = d_means3D; a.d_means2D = d_means2D; a.d_shs = d_shs; a.d_colors = d_colors;
     a.d_opac = d_opacities; a.d_scales = d_scales; a.d_rots = d_rotations; a.d_cov3d = d_cov3D;
+    a.num_sms = ds->num_sms;
     a.stream = static_cast<cudaStream_t>(stream);
 
-    if ((rc = check_cuda(cudaMemsetAsync(a.scratch + a.sl.counters, 0, GSR_NCOUNTERS * sizeof(uint32_t), a.stream), "memset"))) return rc;
-    if ((rc = check_cuda(cudaMemsetAsync(a.scratch + a.sl.dgeom, 0, (size_t)prm->P * 12 * sizeof(float), a.stream), "memset"))) return rc;
+    // no memsets: the work-queue counters and the gradient accumulators live in `saved`, zeroed by
+    // the forward and restored to zero by project_bwd
     prof_mark_bwd(0, a.stream);
-    if ((rc = check_cuda(gsr_launch_composite_bwd(a), "composite_bwd"))) return rc;
+    GSR_RANGE_PUSH("b200gsr.composite_bwd");
+    rc = check_cuda(gsr_launch_composite_bwd(a), "composite_bwd");
+    GSR_RANGE_POP();
+    if (rc) return rc;
     prof_mark_bwd(1, a.stream);
-    if ((rc = check_cuda(gsr_launch_project_bwd(a), "project_bwd"))) return rc;
+    GSR_RANGE_PUSH("b200gsr.project_bwd");
+    rc = check_cuda(gsr_launch_project_bwd(a), "project_bwd");
+    GSR_RANGE_POP();
+    if (rc) return rc;
     prof_mark_bwd(2, a.stream);
     if (g_prof.max_calls > 0 && g_prof.nbwd < g_prof.max_calls) ++g_prof.nbwd;
     return B200GSR_OK;

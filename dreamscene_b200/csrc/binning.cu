@@ -102,6 +102,7 @@ scan_order_kernel(int ntiles, int ncopies, uint32_t max_pairs, const uint32_t* _
         }
         header[GSR_H_NUM_BIG] = nbig;   // upper bound: includes n == 4096 exactly (clz 19)
         header[GSR_H_NUM_NONEMPTY] = run - bucket_cnt[32];
+        for (int k = 0; k < GSR_NQUEUE; ++k) header[GSR_H_BWD_QUEUE + k] = 0u;
         if (host_notify != nullptr) {   // mapped pinned host memory: tell the host the pair count now
             host_notify[1] = total;
             host_notify[2] = total > max_pairs ? 1u : 0u;
@@ -200,6 +201,8 @@ scan_order_fast_kernel(int ntiles, uint32_t max_pairs, const uint32_t* __restric
             header[GSR_H_OVERFLOW] = total > max_pairs ? 1u : 0u;
             header[GSR_H_NUM_BIG] = nbig;
             header[GSR_H_NUM_NONEMPTY] = nonempty;
+#pragma unroll
+            for (int k = 0; k < GSR_NQUEUE; ++k) header[GSR_H_BWD_QUEUE + k] = 0u;
             if (host_notify != nullptr) {   // mapped pinned host memory: tell the host the pair count now
                 host_notify[1] = total;
                 host_notify[2] = total > max_pairs ? 1u : 0u;
@@ -688,8 +691,8 @@ cudaError_t gsr_launch_scan(const GsrFwdArgs& a) {
     const BinPtrs b = bin_ptrs(a);
     if (gsr_use_multisplit(b.grid.ntiles)) {
         // static + dynamic shared memory can exceed the 48 KB default at the top of the range
-        cudaError_t e = cudaFuncSetAttribute(scan_order_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             GSR_MS_MAX_TILES * (int)sizeof(uint32_t));
+        static std::atomic<unsigned long long> attr_done{0};
+        cudaError_t e = gsr_smem_once(scan_order_fast_kernel, GSR_MS_MAX_TILES * (int)sizeof(uint32_t), attr_done);
         if (e != cudaSuccess) return e;
         scan_order_fast_kernel<<<1, 1024, b.grid.ntiles * sizeof(uint32_t), a.stream>>>(b.grid.ntiles, a.max_pairs, b.tile_count, b.tile_start,
                                                           b.tile_cursor, b.work_order, b.header, a.host_notify,
@@ -708,9 +711,10 @@ static cudaError_t launch_multisplit(const GsrFwdArgs& a, const BinPtrs& b, bool
     if (P == 0) return cudaSuccess;
     const int per = 1024 * GSR_MS_ITEMS;
     const int smem = 2 * b.grid.ntiles * (int)sizeof(uint32_t);
-    cudaError_t e = scatter
-        ? cudaFuncSetAttribute(multisplit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-        : cudaFuncSetAttribute(multisplit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int smem_max = 2 * GSR_MS_MAX_TILES * (int)sizeof(uint32_t);
+    static std::atomic<unsigned long long> done_scatter{0}, done_count{0};
+    cudaError_t e = scatter ? gsr_smem_once(multisplit_kernel<true>, smem_max, done_scatter)
+                            : gsr_smem_once(multisplit_kernel<false>, smem_max, done_count);
     if (e != cudaSuccess) return e;
     if (scatter)
         multisplit_kernel<true><<<(P + per - 1) / per, 1024, smem, a.stream>>>(
@@ -745,16 +749,12 @@ cudaError_t gsr_launch_scatter(const GsrFwdArgs& a) {
 cudaError_t gsr_launch_sort(const GsrFwdArgs& a, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join) {
     const BinPtrs b = bin_ptrs(a);
     const int big_smem = (int)sizeof(SortSmemBig), small_smem = (int)sizeof(SortSmemSmall);
-    cudaError_t e = cudaFuncSetAttribute(sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem);
+    static std::atomic<unsigned long long> done_big{0}, done_small{0};
+    cudaError_t e = gsr_smem_once(sort_big_kernel, big_smem, done_big);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(sort_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem);
+    e = gsr_smem_once(sort_small_kernel, small_smem, done_small);
     if (e != cudaSuccess) return e;
-    int nsm = 148;
-    {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int nsm = a.num_sms;
     const int small_grid = min(b.grid.ntiles, nsm * 4);
     const int big_grid = min(b.grid.ntiles, nsm);
     cudaStream_t s_small = a.stream;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 
 #include "../../include/b200gsr.h"
 
@@ -22,7 +23,7 @@ struct __align__(16) GsrRec {
     // part 0: everything the per-warp cull test needs
     float px, py;   // pixel-space mean
     uint32_t ext;   // half2 (ext_x, ext_y): conservative half extents of {alpha >= 1/255}
-    float A;        // scaled conic: log2(G) = A*dx*dx + B*dx*dy + C*dy*dy
+    float A;        // scaled conic: log2(G) = A*dx*dx + B*dx*dy + C*dy*dy  (GSR_EXACT_EXP: raw conic.x)
     // part 1
     float B, C;     //   A = -0.5*log2e*conic.x, B = -log2e*conic.y, C = -0.5*log2e*conic.z
     float opacity;
@@ -45,15 +46,19 @@ __host__ __device__ inline GsrTileGrid gsr_grid(int H, int W) {
     return g;
 }
 
-// header words in the saved buffer
+// header words in the saved buffer (uint32[GSR_H_WORDS])
 enum { GSR_H_NUM_PAIRS = 0, GSR_H_MAX_PAIRS = 1, GSR_H_NUM_TILES = 2, GSR_H_OVERFLOW = 3,
-       GSR_H_NUM_BIG = 4, GSR_H_NUM_NONEMPTY = 5 };
+       GSR_H_NUM_BIG = 4, GSR_H_NUM_NONEMPTY = 5,
+       GSR_H_BWD_QUEUE = 8,       // [8, 8+GSR_NQUEUE): work-queue counters of composite_bwd; zeroed by the
+                                  // forward's scan kernel and restored to zero by project_bwd, so a saved
+                                  // buffer can be back-propagated any number of times without a memset
+       GSR_H_WORDS = 32 };
 // counters in scratch
 // The tile work queue is split into GSR_NQUEUE sub-queues (tile w lives in queue w % NQUEUE): one
 // shared counter would serialise every fetch at the ~30 ns same-address L2 atomic rate.
 #define GSR_NQUEUE 8
 #define GSR_NCOUNTERS 128
-enum { GSR_C_FWD_QUEUE = 0, GSR_C_BWD_QUEUE = GSR_NQUEUE };
+enum { GSR_C_FWD_QUEUE = 0 };
 
 #define GSR_SORT_SMALL_MAX 4096   // keys sorted by the 256-thread kernel (256 x 16 items)
 #define GSR_SORT_BIG_CHUNK 16384  // keys per smem chunk of the 1024-thread kernel (1024 x 16 items)
@@ -76,6 +81,18 @@ __device__ __forceinline__ void stg_na_f4(void* p, float4 v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// Default build: exp via ONE MUFU (ex2.approx on a conic pre-scaled by log2 e), T recovery in the
+// backward via rcp.approx.  -DGSR_EXACT_EXP builds the parity-diagnostic variant
+// (libb200gsr_exact.so): the record keeps the UNSCALED conic, the exponent is evaluated with
+// individually rounded fp32 ops in the oracle's operation order (oracle/splat_ref.py::composite),
+// exp is expf() and the reciprocal an IEEE division.  It exists to show that the forward outliers
+// against the oracle are exp-approximation artefacts at the discontinuous 1/255 and 1e-4 tests
+// (profiles/r02_parity_stats.json) and what the approximation buys (ms).
+#ifdef GSR_EXACT_EXP
+#define GSR_PX_GRAD_SCALE 1.0f
+__device__ __forceinline__ float rcp_approx(float x) { return __fdiv_rn(1.0f, x); }
+#else
+#define GSR_PX_GRAD_SCALE GSR_LN2
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -86,6 +103,7 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+#endif
 
 // ---- shared-memory address helper (cp.async destinations) ----------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -121,6 +139,8 @@ struct GsrFwdArgs {
     uint32_t max_pairs;
     uint32_t* host_notify;
     uint32_t notify_seq;
+    uint32_t flags;        // B200GSR_FWD_*
+    int num_sms;           // of the current device (cached per device in api.cu)
     cudaStream_t stream;
 };
 
@@ -129,14 +149,29 @@ struct GsrBwdArgs {
     const float *means3D, *shs, *colors, *opac, *scales, *rots, *cov3d;
     const int32_t* radii;
     const float *out_depth_alpha, *dL_dcolor, *dL_ddepth_alpha;
-    const uint8_t* saved;
-    uint8_t* scratch;
+    uint8_t* saved;     // counters + gradient accumulators inside are consumed and restored
+    uint8_t* scratch;   // unused (kept for layout symmetry)
     b200gsr_scratch_layout sl;
     b200gsr_saved_layout vl;
     uint32_t max_pairs;
     float *d_means3D, *d_means2D, *d_shs, *d_colors, *d_opac, *d_scales, *d_rots, *d_cov3d;
+    int num_sms;
     cudaStream_t stream;
 };
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) instead of on every
+// launch: `done` is a per-call-site bit mask indexed by device ordinal.
+template <typename F>
+inline cudaError_t gsr_smem_once(F func, int bytes, std::atomic<unsigned long long>& done) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+}
 
 cudaError_t gsr_launch_project(const GsrFwdArgs& a);
 cudaError_t gsr_launch_count(const GsrFwdArgs& a);         // multisplit path: per-tile pair counts

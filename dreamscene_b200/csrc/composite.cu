@@ -70,9 +70,16 @@ __device__ __forceinline__ PairEval eval_pair(float px, float py, float A, float
     PairEval e;
     e.dx = __fsub_rn(px, X);
     e.dy = __fsub_rn(py, Y);
+#ifdef GSR_EXACT_EXP
+    // oracle order (splat_ref.py::composite): power = -0.5*(A*dx*dx + C*dy*dy) - B*dx*dy, raw conic
+    const float qs = __fadd_rn(__fmul_rn(__fmul_rn(A, e.dx), e.dx), __fmul_rn(__fmul_rn(C, e.dy), e.dy));
+    const float p2 = __fsub_rn(__fmul_rn(-0.5f, qs), __fmul_rn(__fmul_rn(B, e.dx), e.dy));
+    e.G = expf(fminf(p2, 0.0f));
+#else
     const float u = __fmaf_rn(A, e.dx, __fmul_rn(B, e.dy));
     const float p2 = __fmaf_rn(__fmul_rn(C, e.dy), e.dy, __fmul_rn(u, e.dx));
     e.G = ex2_approx(p2);
+#endif
     e.alpha = fminf(GSR_ALPHA_MAX, __fmul_rn(opacity, e.G));
     e.valid = (p2 <= 0.0f) && (e.alpha >= GSR_ALPHA_MIN);
     return e;
@@ -386,8 +393,13 @@ composite_bwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restric
                     accB = fmaf(e.alpha, q2.z - accB, accB);
                     accD = fmaf(e.alpha, q1.w - accD, accD);
                     const float gG = q1.z * dLda * e.G;   // dL/dG * G (no zeroing under the 0.99 clamp)
+#ifdef GSR_EXACT_EXP
+                    const float gxs = -(q0.w * e.dx + q1.x * e.dy);    // d ln G / d px, raw conic
+                    const float gys = -(q1.y * e.dy + q1.x * e.dx);
+#else
                     const float gxs = 2.0f * q0.w * e.dx + q1.x * e.dy;
                     const float gys = 2.0f * q1.y * e.dy + q1.x * e.dx;
+#endif
                     vv[0] = gG * gxs; vv[1] = gG * gys;
                     vv[2] = gG * e.dx * e.dx; vv[3] = gG * e.dx * e.dy; vv[4] = gG * e.dy * e.dy;
                     vv[5] = e.G * dLda;
@@ -408,13 +420,6 @@ composite_bwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restric
 }
 
 }  // namespace
-
-static int g_num_sms() {
-    int dev = 0, nsm = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    return nsm;
-}
 
 struct CompPtrs {
     GsrTileGrid grid;
@@ -438,7 +443,8 @@ static CompPtrs comp_ptrs(const uint8_t* saved, const b200gsr_saved_layout& vl, 
 template <bool SCORE>
 static cudaError_t launch_fwd(const GsrFwdArgs& a, int nblocks, const CompPtrs& c, uint32_t* queue) {
     const int smem = (int)sizeof(SmemCta);
-    cudaError_t e = cudaFuncSetAttribute(composite_fwd_kernel<SCORE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    static std::atomic<unsigned long long> attr_done{0};
+    cudaError_t e = gsr_smem_once(composite_fwd_kernel<SCORE, 1>, smem, attr_done);
     if (e != cudaSuccess) return e;
     composite_fwd_kernel<SCORE, 1><<<nblocks, 256, smem, a.stream>>>(
         a.prm.image_height, a.prm.image_width, c.grid.gx, c.grid.ntiles, c.header, c.work_order, c.tile_start,
@@ -450,15 +456,16 @@ cudaError_t gsr_launch_composite_fwd(const GsrFwdArgs& a) {
     const CompPtrs c = comp_ptrs(a.saved, a.vl, a.prm.image_height, a.prm.image_width);
     if (c.grid.ntiles == 0) return cudaSuccess;
     uint32_t* queue = reinterpret_cast<uint32_t*>(a.scratch + a.sl.counters) + GSR_C_FWD_QUEUE;
-    const int nblocks = min(c.grid.ntiles, g_num_sms() * 6);
+    const int nblocks = min(c.grid.ntiles, a.num_sms * 6);
     return a.prm.score_flag ? launch_fwd<true>(a, nblocks, c, queue) : launch_fwd<false>(a, nblocks, c, queue);
 }
 
 template <int kSlots, int kMinCtas>
 static cudaError_t launch_bwd(const GsrBwdArgs& a, const CompPtrs& c, uint32_t* queue, float* dgeom) {
     const int smem = (int)sizeof(SmemRing<kSlots>);
-    const int nblocks = min(c.grid.ntiles, g_num_sms() * kMinCtas);
-    cudaError_t e = cudaFuncSetAttribute(composite_bwd_kernel<kSlots, kMinCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int nblocks = min(c.grid.ntiles, a.num_sms * kMinCtas);
+    static std::atomic<unsigned long long> attr_done{0};
+    cudaError_t e = gsr_smem_once(composite_bwd_kernel<kSlots, kMinCtas>, smem, attr_done);
     if (e != cudaSuccess) return e;
     composite_bwd_kernel<kSlots, kMinCtas><<<nblocks, kWarps * 32, smem, a.stream>>>(
         a.prm.image_height, a.prm.image_width, c.grid.gx, c.grid.ntiles, c.header, c.work_order, c.tile_start,
@@ -469,8 +476,8 @@ static cudaError_t launch_bwd(const GsrBwdArgs& a, const CompPtrs& c, uint32_t* 
 cudaError_t gsr_launch_composite_bwd(const GsrBwdArgs& a) {
     const CompPtrs c = comp_ptrs(a.saved, a.vl, a.prm.image_height, a.prm.image_width);
     if (c.grid.ntiles == 0) return cudaSuccess;
-    uint32_t* queue = reinterpret_cast<uint32_t*>(a.scratch + a.sl.counters) + GSR_C_BWD_QUEUE;
-    float* dgeom = reinterpret_cast<float*>(a.scratch + a.sl.dgeom);
+    uint32_t* queue = reinterpret_cast<uint32_t*>(a.saved + a.vl.header) + GSR_H_BWD_QUEUE;
+    float* dgeom = reinterpret_cast<float*>(a.saved + a.vl.dgeom);
     // ring depth x CTAs/SM: tuned default 3 x 4 (measured 0.253 ms; 4:0.260, 6:0.273, 8:0.282);
     // B200GSR_BWD_SLOTS=2|25|35|4 selects other variants for A/B runs
     static const int slots = [] { const char* e = getenv("B200GSR_BWD_SLOTS"); return e ? atoi(e) : 3; }();

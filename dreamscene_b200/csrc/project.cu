@@ -268,12 +268,16 @@ project_sh_kernel(b200gsr_params p, const float* __restrict__ means3D,
                   const float* __restrict__ opac, const float* __restrict__ scales,
                   const float* __restrict__ rots, const float* __restrict__ cov3d,
                   int32_t* __restrict__ radii, uint4* __restrict__ rectdepth,
-                  GsrRec* __restrict__ geom, uint32_t* __restrict__ tile_count) {
+                  GsrRec* __restrict__ geom, uint32_t* __restrict__ tile_count,
+                  uint32_t* __restrict__ zero_words, int num_zero_words, float* __restrict__ dgeom) {
     extern __shared__ __align__(16) float sh_buf[];
     __shared__ uint8_t vis_s[kBlock];
     const int g0 = blockIdx.x * kBlock;
     const int i = g0 + threadIdx.x;
     const bool active = i < p.P;
+    // prologue (replaces a memset node): zero the work-queue + per-tile pair counters that the
+    // count kernel launched right after this one accumulates into
+    for (int zw = i; zw < num_zero_words; zw += gridDim.x * kBlock) zero_words[zw] = 0u;
     Cam C;
     load_cam(p, C);
     const GsrTileGrid grid = gsr_grid(p.image_height, p.image_width);
@@ -360,15 +364,26 @@ project_sh_kernel(b200gsr_params p, const float* __restrict__ means3D,
     const __half2 eh = __floats2half2_rn(ex, ey);
     GsrRec rec;
     rec.px = g.px; rec.py = g.py;
+#ifdef GSR_EXACT_EXP
+    rec.A = MUL(g.c, g.det_inv);                      // raw conic (x, y, z) as the oracle forms it
+    rec.B = MUL(-g.b, g.det_inv);
+    rec.C = MUL(g.a, g.det_inv);
+#else
     rec.A = -0.5f * GSR_LOG2E * MUL(g.c, g.det_inv);
     rec.B = GSR_LOG2E * MUL(g.b, g.det_inv);          // -log2e * conic.y, conic.y = -b/det
     rec.C = -0.5f * GSR_LOG2E * MUL(g.a, g.det_inv);
+#endif
     rec.opacity = o; rec.depth = g.tz; rec.idx = (uint32_t)i;
     rec.r = rgb[0]; rec.g = rgb[1]; rec.b = rgb[2];
     rec.ext = *reinterpret_cast<const uint32_t*>(&eh);
     float4* dst = reinterpret_cast<float4*>(geom + i);
     const float4* src = reinterpret_cast<const float4*>(&rec);
     dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+    if (dgeom != nullptr) {   // gradient accumulators of this (visible) Gaussian start at zero
+        float4* dz = reinterpret_cast<float4*>(dgeom + 12 * (size_t)i);
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        dz[0] = z4; dz[1] = z4; dz[2] = z4;
+    }
 }
 
 // =========================================================================================
@@ -383,7 +398,7 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
                    const float* __restrict__ shs, const float* __restrict__ colors,
                    const float* __restrict__ scales, const float* __restrict__ rots,
                    const float* __restrict__ cov3d, const int32_t* __restrict__ radii,
-                   const float* __restrict__ dgeom,
+                   float* __restrict__ dgeom, uint32_t* __restrict__ bwd_queue,
                    float* __restrict__ d_means3D, float* __restrict__ d_means2D,
                    float* __restrict__ d_shs, float* __restrict__ d_colors,
                    float* __restrict__ d_opac, float* __restrict__ d_scales,
@@ -411,6 +426,8 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
     float drot[4] = {0.f, 0.f, 0.f, 0.f};
     float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float dcol[3] = {0.f, 0.f, 0.f};
+    // composite_bwd (the previous kernel on the stream) has drained its work queue: reset it
+    if (blockIdx.x == 0 && threadIdx.x < GSR_NQUEUE) bwd_queue[threadIdx.x] = 0u;
 
     if (vis) {
         Cam C;
@@ -420,13 +437,15 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
         Geo g;
         geo_view(C, x, y, z, g);
         geo_rest(C, p, x, y, z, scales, rots, cov3d, i, g);
-        const float4 a0 = ldg_f4(dgeom + 12 * (size_t)i);
-        const float4 a1 = ldg_f4(dgeom + 12 * (size_t)i + 4);
-        const float4 a2 = ldg_f4(dgeom + 12 * (size_t)i + 8);
+        // read-and-clear: the accumulators are zero again for the next backward over this `saved`
+        float4* dg = reinterpret_cast<float4*>(dgeom + 12 * (size_t)i);
+        const float4 a0 = dg[0], a1 = dg[1], a2 = dg[2];
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        dg[0] = z4; dg[1] = z4; dg[2] = z4;
         const float Wf = (float)p.image_width, Hf = (float)p.image_height;
 
         // ---- mean2D -------------------------------------------------------------------------
-        const float dpx = GSR_LN2 * a0.x, dpy = GSR_LN2 * a0.y;   // dL/d(pixel mean)
+        const float dpx = GSR_PX_GRAD_SCALE * a0.x, dpy = GSR_PX_GRAD_SCALE * a0.y;   // dL/d(pixel mean)
         const float dndcx = dpx * 0.5f * Wf, dndcy = dpy * 0.5f * Hf;
         dm2[0] = dndcx; dm2[1] = dndcy;
         const float pw = g.pw, pw2 = pw * pw;
@@ -659,11 +678,18 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
 
 template <int MT>
 static void launch_project_sh(const GsrFwdArgs& a, int P, size_t smem) {
+    // multisplit path: counters + the single per-tile counter array are zeroed in the prologue
+    // (api.cu issues a memset instead on the large-grid fallback, where this kernel counts itself)
+    const GsrTileGrid tg = gsr_grid(a.prm.image_height, a.prm.image_width);
+    const int nzero = gsr_use_multisplit(tg.ntiles)
+        ? (int)((a.sl.tile_count + (size_t)tg.ntiles * sizeof(uint32_t)) / sizeof(uint32_t)) : 0;
     project_sh_kernel<MT><<<(P + kBlock - 1) / kBlock, kBlock, smem, a.stream>>>(
         a.prm, a.means3D, a.shs, a.colors, a.opac, a.scales, a.rots, a.cov3d, a.radii,
         reinterpret_cast<uint4*>(a.scratch + a.sl.rectdepth),
         reinterpret_cast<GsrRec*>(a.saved + a.vl.geom),
-        reinterpret_cast<uint32_t*>(a.scratch + a.sl.tile_count));
+        reinterpret_cast<uint32_t*>(a.scratch + a.sl.tile_count),
+        reinterpret_cast<uint32_t*>(a.scratch), nzero,
+        (a.flags & B200GSR_FWD_NO_BACKWARD) ? nullptr : reinterpret_cast<float*>(a.saved + a.vl.dgeom));
 }
 
 cudaError_t gsr_launch_project(const GsrFwdArgs& a) {
@@ -680,7 +706,8 @@ template <int MT>
 static void launch_project_bwd(const GsrBwdArgs& a, int P, size_t smem) {
     project_bwd_kernel<MT><<<(P + kBlock - 1) / kBlock, kBlock, smem, a.stream>>>(
         a.prm, a.means3D, a.shs, a.colors, a.scales, a.rots, a.cov3d, a.radii,
-        reinterpret_cast<const float*>(a.scratch + a.sl.dgeom), a.d_means3D, a.d_means2D, a.d_shs,
+        reinterpret_cast<float*>(a.saved + a.vl.dgeom),
+        reinterpret_cast<uint32_t*>(a.saved + a.vl.header) + GSR_H_BWD_QUEUE, a.d_means3D, a.d_means2D, a.d_shs,
         a.d_colors, a.d_opac, a.d_scales, a.d_rots, a.d_cov3d);
 }
 

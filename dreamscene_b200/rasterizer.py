@@ -17,6 +17,7 @@ include/b200gsr.h; PyTorch provides device memory, the stream and autograd plumb
 from __future__ import annotations
 
 import ctypes as C
+import os
 import time
 from typing import NamedTuple, Optional
 
@@ -43,46 +44,138 @@ class GaussianRasterizationSettings(NamedTuple):
 
 
 # ------------------------------------------------------------------------------------------
-# Workspace: one transient scratch buffer + pair-capacity estimate per (device, stream).
+# Workspaces.  Per DEVICE: the pair-capacity high-water mark, the pinned device-mapped notify ring
+# and the deferred overflow checks.  Per (device, stream): one transient scratch buffer.
 # ------------------------------------------------------------------------------------------
-class _Workspace:
+_MIN_CAPACITY = 1 << 20
+_MIN_PAIRS_PER_GAUSSIAN = 4
+_POLL_TIMEOUT_S = 60.0
+_NOTIFY_SLOTS = 256
+
+
+class PairCapacityOverflow(RuntimeError):
+    """Raised (asynchronous mode only) when an EARLIER forward produced more (tile, Gaussian) pairs
+    than its key buffer could hold: that call's images and gradients are invalid."""
+
+
+class _Device:
     def __init__(self, device: torch.device):
         self.device = device
-        self.scratch: Optional[torch.Tensor] = None
-        self.capacity = 0                       # pair capacity used for the next call
-        self.notify = torch.zeros(4, dtype=torch.int32).pin_memory()   # device-mapped host words
+        self.capacity = 0            # pair capacity used for the next call (only ever grows)
+        self.user_capacity = False   # set by set_workspace_capacity: trust it, never wait on it
+        self.last_pairs = 0          # pair count of the most recent RESOLVED forward
         self.seq = 0
-        self.last_pairs = 0
+        self.notify: Optional[torch.Tensor] = None   # int32[_NOTIFY_SLOTS, 4] pinned, device-mapped
+        self.notify_np = None
+        self.free_slots: list = []
+        self.pending: list = []      # [(slot, seq, capacity)] forwards whose pair count is not read yet
+        self.scratch: dict = {}      # stream handle -> uint8 tensor
 
-    def ensure_scratch(self, nbytes: int) -> torch.Tensor:
-        if self.scratch is None or self.scratch.numel() < nbytes:
-            self.scratch = torch.empty(int(nbytes * 1.1) + 4096, dtype=torch.uint8, device=self.device)
-        return self.scratch
+    def ensure_notify(self):
+        if self.notify is None:
+            self.notify = torch.zeros(_NOTIFY_SLOTS, 4, dtype=torch.int32).pin_memory()
+            self.notify_np = self.notify.numpy()      # shares the pinned pages: plain loads, no tensor ops
+            self.free_slots = list(range(_NOTIFY_SLOTS - 1, -1, -1))
+
+    def ensure_scratch(self, stream: int, nbytes: int) -> torch.Tensor:
+        t = self.scratch.get(stream)
+        if t is None or t.numel() < nbytes:
+            t = self.scratch[stream] = torch.empty(int(nbytes * 1.1) + 4096, dtype=torch.uint8, device=self.device)
+        return t
+
+    def next_seq(self) -> int:
+        self.seq = (self.seq + 1) & 0x7FFFFFFF or 1
+        return self.seq
 
 
-_workspaces: dict = {}
-_MIN_CAPACITY = 1 << 20
-_POLL_TIMEOUT_S = 60.0
+_devices: dict = {}
+_pair_mode = os.environ.get("B200GSR_PAIR_MODE", "async")
 
 
-def _workspace(device: torch.device) -> _Workspace:
-    stream = torch.cuda.current_stream(device).cuda_stream
-    key = (device.index if device.index is not None else torch.cuda.current_device(), stream)
-    ws = _workspaces.get(key)
-    if ws is None:
-        ws = _workspaces[key] = _Workspace(device)
-    return ws
+def _device_state(device: torch.device) -> _Device:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    d = _devices.get(idx)
+    if d is None:
+        d = _devices[idx] = _Device(torch.device("cuda", idx))
+    return d
+
+
+def set_pair_count_mode(mode: str) -> None:
+    """How forward learns the (tile, Gaussian) pair count D that sizes the sorted key buffer.
+
+    "sync"  : after enqueueing all kernels the host waits for the tile scan (the first ~10% of the
+              forward) to report D through a device-mapped host word and transparently re-issues the
+              call if D exceeded the capacity.  Always exact; same stream-position sync as upstream's
+              num_rendered D2H copy.
+    "async" : (default) no host wait at all.  The capacity is 2x the largest D seen on the device
+              (at least 4 pairs per Gaussian); the count of every forward is read lazily - without
+              blocking - at later API calls, and an overflow (practically impossible with that
+              head-room) raises PairCapacityOverflow then.  The first forward on a device, which
+              establishes the capacity, is always synchronous unless set_workspace_capacity was called.
+    Also settable with the environment variable B200GSR_PAIR_MODE."""
+    global _pair_mode
+    if mode not in ("sync", "async"):
+        raise ValueError("mode must be 'sync' or 'async'")
+    _pair_mode = mode
 
 
 def set_workspace_capacity(max_pairs: int, device=None) -> None:
-    """Optional: pre-size the (tile, Gaussian) pair capacity of the current stream's workspace."""
+    """Optional: pre-size the (tile, Gaussian) pair capacity of a device (required before capturing
+    the rasterizer into a CUDA graph on a device that has not rendered eagerly yet)."""
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    _workspace(dev).capacity = int(max_pairs)
+    d = _device_state(dev)
+    d.capacity = int(max_pairs)
+    d.user_capacity = True
 
 
 def _round_cap(n: int) -> int:
     g = 1 << 18
     return max(_MIN_CAPACITY, (int(n) + g - 1) // g * g)
+
+
+def _resolve_pending(d: _Device, block: bool = False) -> None:
+    """Read the pair counts the device has reported so far (never waits unless `block`)."""
+    if not d.pending:
+        return
+    n = d.notify_np
+    still, overflow = [], None
+    t0 = time.perf_counter()
+    for slot, seq, cap in d.pending:
+        while block and int(n[slot, 0]) != seq:
+            if time.perf_counter() - t0 > _POLL_TIMEOUT_S:
+                torch.cuda.synchronize(d.device)
+                if int(n[slot, 0]) != seq:
+                    raise RuntimeError("b200gsr: device never reported a pair count")
+        if int(n[slot, 0]) != seq:
+            still.append((slot, seq, cap))
+            continue
+        pairs = int(n[slot, 1]) & 0xFFFFFFFF
+        d.free_slots.append(slot)
+        d.last_pairs = pairs
+        d.capacity = max(d.capacity, _round_cap(2 * pairs))
+        if pairs > cap:
+            overflow = (pairs, cap)
+    d.pending = still
+    if overflow is not None:
+        raise PairCapacityOverflow(
+            f"b200gsr: an earlier forward produced {overflow[0]} (tile, Gaussian) pairs but its key buffer held "
+            f"{overflow[1]}; its images/gradients are invalid. The capacity has been raised to {d.capacity}; "
+            "re-run the step, or call set_workspace_capacity()/set_pair_count_mode('sync').")
+
+
+def flush_checks(device=None) -> None:
+    """Wait for every forward issued so far to report its pair count (raises on overflow)."""
+    for d in list(_devices.values()):
+        if device is None or d.device == torch.device(device):
+            _resolve_pending(d, block=True)
+
+
+def last_pair_count(device=None) -> int:
+    """Pair count D of the most recent forward on the device (waits for it to be reported)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    d = _device_state(dev)
+    _resolve_pending(d, block=True)
+    return d.last_pairs
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -100,10 +193,15 @@ def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return t
 
 
+def _const(t: torch.Tensor, dev) -> torch.Tensor:
+    # per-view constants live on the Gaussians' device (upstream requires CUDA tensors here too)
+    if t.device != dev or t.dtype != torch.float32 or not t.is_contiguous() or t.requires_grad:
+        t = t.detach().to(dev, torch.float32).contiguous()
+    return t
+
+
 def _make_params(rs: GaussianRasterizationSettings, P: int, M: int, keep: list, dev) -> _lib.Params:
-    # the per-view constants live on the Gaussians' device (upstream requires CUDA tensors here too)
-    bg = _f32c(rs.bg.detach().to(dev)); vm = _f32c(rs.viewmatrix.detach().to(dev))
-    pm = _f32c(rs.projmatrix.detach().to(dev)); cp = _f32c(rs.campos.detach().to(dev))
+    bg, vm, pm, cp = _const(rs.bg, dev), _const(rs.viewmatrix, dev), _const(rs.projmatrix, dev), _const(rs.campos, dev)
     keep.extend([bg, vm, pm, cp])
     return _lib.Params(P, M, int(rs.sh_degree), int(rs.image_height), int(rs.image_width),
                        float(rs.tanfovx), float(rs.tanfovy), float(rs.scale_modifier),
@@ -113,10 +211,24 @@ def _make_params(rs: GaussianRasterizationSettings, P: int, M: int, keep: list, 
 
 class _State:
     """Everything backward needs that is not a tensor input."""
-    __slots__ = ("params_keep", "P", "M", "capacity", "saved", "rs")
+    __slots__ = ("params_keep", "P", "M", "capacity", "saved", "rs", "with_backward")
 
 
-def _forward_impl(rs, means3D, shs, colors, opac, scales, rots, cov3d):
+_layout_cache: dict = {}
+
+
+def _layouts(P, H, W, cap, with_backward):
+    key = (P, H, W, cap, with_backward)
+    r = _layout_cache.get(key)
+    if r is None:
+        if len(_layout_cache) > 256:
+            _layout_cache.clear()
+        r = _layout_cache[key] = (_lib.scratch_layout(P, H, W, cap).total,
+                                  _lib.saved_layout(P, H, W, cap, with_backward).total)
+    return r
+
+
+def _forward_impl(rs, means3D, shs, colors, opac, scales, rots, cov3d, with_backward=True):
     lib = _lib.load()
     dev = means3D.device
     if dev.type != "cuda":
@@ -125,53 +237,78 @@ def _forward_impl(rs, means3D, shs, colors, opac, scales, rots, cov3d):
     P = int(means3D.shape[0])
     M = int(shs.shape[1]) if shs is not None else 0
     H, W = int(rs.image_height), int(rs.image_width)
+    d = _device_state(dev)
+    capturing = torch.cuda.is_current_stream_capturing()
+    if not capturing:
+        d.ensure_notify()
+        _resolve_pending(d)               # non-blocking: may raise PairCapacityOverflow for an earlier call
     keep: list = []
-    prm = _make_params(rs, P, M, keep, dev)
-    color = torch.empty(3, H, W, dtype=torch.float32, device=dev)
-    depth_alpha = torch.empty(2, H, W, dtype=torch.float32, device=dev)
-    radii = torch.empty(P, dtype=torch.int32, device=dev)
-    score = torch.zeros(P, dtype=torch.float32, device=dev) if rs.score_flag else None
-    ws = _workspace(dev)
-    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    cap = ws.capacity if ws.capacity > 0 else _round_cap(6 * P)
-    if torch.cuda.current_device() != dev.index:
-        torch.cuda.set_device(dev)        # the library launches on the CURRENT device (callers use cuda:0)
-    while True:
-        sl = _lib.scratch_layout(P, H, W, cap)
-        vl = _lib.saved_layout(P, H, W, cap)
-        scratch = ws.ensure_scratch(sl.total)
-        saved = torch.empty(vl.total, dtype=torch.uint8, device=dev)
-        ws.seq = (ws.seq + 1) & 0x7FFFFFFF or 1
-        rc = lib.b200gsr_forward(C.byref(prm), _ptr(means3D), _ptr(shs), _ptr(colors), _ptr(opac),
-                                 _ptr(scales), _ptr(rots), _ptr(cov3d), _ptr(color), _ptr(depth_alpha),
-                                 _ptr(radii), _ptr(score), _ptr(scratch), scratch.numel(), _ptr(saved),
-                                 saved.numel(), cap, C.c_void_p(ws.notify.data_ptr()), ws.seq, stream)
-        if rc:
-            msg = _lib.last_error()
-            if rc == -1:
-                raise Exception(msg)
-            raise RuntimeError(f"b200gsr_forward failed ({rc}): {msg}")
-        # Wait only for the tile scan (project + scan kernels); sort/composite keep running.
-        t0 = time.perf_counter()
-        n = ws.notify
-        while int(n[0]) != ws.seq:
-            if time.perf_counter() - t0 > _POLL_TIMEOUT_S:
-                torch.cuda.synchronize(dev)
-                if int(n[0]) == ws.seq:
-                    break
-                raise RuntimeError("b200gsr_forward: device never reported the pair count")
-        pairs = int(n[1]) & 0xFFFFFFFF
-        ws.last_pairs = pairs
-        if pairs <= cap:
-            # high-water mark with 25% head-room: the capacity only costs 8 B per pair in `saved`, and
-            # views of one training step differ a lot in pair count (random cameras), so never shrink
-            ws.capacity = max(ws.capacity, _round_cap(int(pairs * 1.25)), _MIN_CAPACITY)
-            break
-        cap = ws.capacity = _round_cap(int(pairs * 1.5))   # overflow: re-issue with enough room
-        if score is not None:
-            score.zero_()
+    with torch.cuda.device(dev):          # the library launches on the CURRENT device; restored on exit
+        prm = _make_params(rs, P, M, keep, dev)
+        color = torch.empty(3, H, W, dtype=torch.float32, device=dev)
+        depth_alpha = torch.empty(2, H, W, dtype=torch.float32, device=dev)
+        radii = torch.empty(P, dtype=torch.int32, device=dev)
+        score = torch.zeros(P, dtype=torch.float32, device=dev) if rs.score_flag else None
+        stream_h = torch.cuda.current_stream(dev).cuda_stream
+        stream = C.c_void_p(stream_h)
+        flags = 0 if with_backward else _lib.FWD_NO_BACKWARD
+        known = d.capacity > 0
+        if capturing and not known:
+            raise RuntimeError("b200gsr: capturing into a CUDA graph needs a known pair capacity: run one eager "
+                               "forward on this device first or call set_workspace_capacity()")
+        cap = _round_cap(max(d.capacity, _MIN_PAIRS_PER_GAUSSIAN * P)) if known else _round_cap(6 * P)
+        # wait for the count only when it is needed: sync mode, or the capacity is a blind first guess
+        wait = (not capturing) and (_pair_mode == "sync" or not known)
+        while True:
+            scratch_bytes, saved_bytes = _layouts(P, H, W, cap, with_backward)
+            scratch = d.ensure_scratch(stream_h, scratch_bytes)
+            saved = torch.empty(saved_bytes, dtype=torch.uint8, device=dev)
+            slot, seq, notify_ptr = -1, 0, None
+            if not capturing:
+                if not d.free_slots:
+                    _resolve_pending(d, block=True)
+                slot, seq = d.free_slots.pop(), d.next_seq()
+                notify_ptr = C.c_void_p(d.notify.data_ptr() + 16 * slot)
+            rc = lib.b200gsr_forward(C.byref(prm), _ptr(means3D), _ptr(shs), _ptr(colors), _ptr(opac),
+                                     _ptr(scales), _ptr(rots), _ptr(cov3d), _ptr(color), _ptr(depth_alpha),
+                                     _ptr(radii), _ptr(score), _ptr(scratch), scratch.numel(), _ptr(saved),
+                                     saved.numel(), cap, flags, notify_ptr, seq, stream)
+            if rc:
+                if slot >= 0:
+                    d.free_slots.append(slot)
+                msg = _lib.last_error()
+                if rc == -1:
+                    raise Exception(msg)
+                raise RuntimeError(f"b200gsr_forward failed ({rc}): {msg}")
+            if capturing:
+                break
+            if not wait:
+                d.pending.append((slot, seq, cap))       # resolved lazily, never blocks the host
+                break
+            # Wait only for the tile scan (project + count + scan kernels); sort/composite keep running.
+            t0 = time.perf_counter()
+            n = d.notify_np
+            while int(n[slot, 0]) != seq:
+                if time.perf_counter() - t0 > _POLL_TIMEOUT_S:
+                    torch.cuda.synchronize(dev)
+                    if int(n[slot, 0]) == seq:
+                        break
+                    raise RuntimeError("b200gsr_forward: device never reported the pair count")
+            pairs = int(n[slot, 1]) & 0xFFFFFFFF
+            d.free_slots.append(slot)
+            d.last_pairs = pairs
+            if pairs <= cap:
+                # high-water mark with 2x head-room: capacity only costs 8 B per pair in `saved`, and
+                # views of one training step differ a lot in pair count (random cameras); never shrinks
+                if not d.user_capacity:
+                    d.capacity = max(d.capacity, _round_cap(2 * pairs))
+                break
+            cap = d.capacity = _round_cap(2 * pairs)   # overflow: re-issue with enough room
+            if score is not None:
+                score.zero_()
     st = _State()
     st.params_keep = keep; st.P = P; st.M = M; st.capacity = cap; st.saved = saved; st.rs = rs
+    st.with_backward = with_backward
     return color, radii, depth_alpha, score, st
 
 
@@ -195,8 +332,11 @@ class _RasterizeGaussians(torch.autograd.Function):
         means3D = _f32c(means3D); sh = _f32c(sh); colors_precomp = _f32c(colors_precomp)
         opacities = _f32c(opacities); scales = _f32c(scales); rotations = _f32c(rotations)
         cov3Ds_precomp = _f32c(cov3Ds_precomp)
+        # under torch.no_grad() / with frozen inputs no backward can follow: skip the accumulators
+        with_backward = any(ctx.needs_input_grad)
         color, radii, depth_alpha, score, st = _forward_impl(
-            raster_settings, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)
+            raster_settings, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+            with_backward=with_backward)
         ctx.st = st
         ctx.has = (sh is not None, colors_precomp is not None, scales is not None, cov3Ds_precomp is not None)
         tensors = [means3D, opacities, radii, depth_alpha]
@@ -250,20 +390,20 @@ class _RasterizeGaussians(torch.autograd.Function):
 
         if P > 0:
             lib = _lib.load()
-            if torch.cuda.current_device() != dev.index:
-                torch.cuda.set_device(dev)
+            if not st.with_backward:
+                raise RuntimeError("b200gsr: backward through a forward that ran without gradient accumulators")
+            if not torch.cuda.is_current_stream_capturing():
+                _resolve_pending(_device_state(dev))      # non-blocking overflow check of earlier forwards
             keep: list = []
-            prm = _make_params(rs, P, M, keep, dev)
-            ws = _workspace(dev)
-            sl = _lib.scratch_layout(P, H, W, st.capacity)
-            scratch = ws.ensure_scratch(sl.total)
-            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            rc = lib.b200gsr_backward(
-                C.byref(prm), _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(opacities), _ptr(scales),
-                _ptr(rots), _ptr(cov3d), _ptr(radii), _ptr(depth_alpha), _ptr(g_color), _ptr(g_da),
-                _ptr(st.saved), st.saved.numel(), _ptr(scratch), scratch.numel(), st.capacity,
-                _ptr(d_means3D), _ptr(d_means2D), _ptr(d_sh), _ptr(d_colors), _ptr(d_opac),
-                _ptr(d_scales), _ptr(d_rots), _ptr(d_cov), stream)
+            with torch.cuda.device(dev):
+                prm = _make_params(rs, P, M, keep, dev)
+                stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+                rc = lib.b200gsr_backward(
+                    C.byref(prm), _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(opacities), _ptr(scales),
+                    _ptr(rots), _ptr(cov3d), _ptr(radii), _ptr(depth_alpha), _ptr(g_color), _ptr(g_da),
+                    _ptr(st.saved), st.saved.numel(), None, 0, st.capacity,
+                    _ptr(d_means3D), _ptr(d_means2D), _ptr(d_sh), _ptr(d_colors), _ptr(d_opac),
+                    _ptr(d_scales), _ptr(d_rots), _ptr(d_cov), stream)
             if rc:
                 raise RuntimeError(f"b200gsr_backward failed ({rc}): {_lib.last_error()}")
             _parallel.maybe_all_reduce(flat)
@@ -287,10 +427,11 @@ class GaussianRasterizer(nn.Module):
         with torch.no_grad():
             pos = _f32c(positions)
             vis = torch.empty(pos.shape[0], dtype=torch.uint8, device=pos.device)
-            vm, pm = _f32c(rs.viewmatrix), _f32c(rs.projmatrix)
-            rc = _lib.load().b200gsr_mark_visible(
-                int(pos.shape[0]), _ptr(pos), _ptr(vm), _ptr(pm), _ptr(vis),
-                C.c_void_p(torch.cuda.current_stream(pos.device).cuda_stream))
+            vm, pm = _const(rs.viewmatrix, pos.device), _const(rs.projmatrix, pos.device)
+            with torch.cuda.device(pos.device):
+                rc = _lib.load().b200gsr_mark_visible(
+                    int(pos.shape[0]), _ptr(pos), _ptr(vm), _ptr(pm), _ptr(vis),
+                    C.c_void_p(torch.cuda.current_stream(pos.device).cuda_stream))
             if rc:
                 raise RuntimeError(f"b200gsr_mark_visible failed ({rc}): {_lib.last_error()}")
         return vis.bool()

@@ -3,8 +3,9 @@
 Recipes restate the reference's initialisers (no reference import):
   * positions: uniform ball, gs_renderer.py:359-367
   * scales: sqrt(mean squared distance to 3 nearest neighbours), gs_renderer.py:590-594
-    (approximated for large P by the expected 3-NN distance of a uniform ball - the exact
-    kNN is init-only upstream and not part of the hot path), times exp(N(0,0.3)) anisotropy
+    (exact k-d tree 3-NN by default = the reference recipe; `exact_knn=False` substitutes the
+    expected 3-NN distance of a uniform ball, which is what round 1 benchmarked and gives ~30%
+    more tile pairs), times exp(N(0,0.3)) anisotropy
   * SH: dc = RGB2SH(U(0,1)) (gs_renderer.py:585, utils/sh_utils.py:122-123), rest N(0,0.05)
 """
 from __future__ import annotations
@@ -18,7 +19,7 @@ SH_C0 = 0.28209479177387814
 
 
 def ball_scene(P: int, radius: float = 0.5, sh_degree_max: int = 3, seed: int = 0,
-               opacity: str = "sigmoid_normal", exact_knn: bool = False):
+               opacity: str = "sigmoid_normal", exact_knn: bool = True):
     """Returns dict of CPU fp32 tensors: means3D[P,3], scales[P,3] (post-exp), rotations[P,4]
     (unit), opacities[P,1] (post-sigmoid), shs[P,M,3]."""
     rng = np.random.RandomState(seed)
@@ -29,9 +30,9 @@ def ball_scene(P: int, radius: float = 0.5, sh_degree_max: int = 3, seed: int = 
     r = radius * np.cbrt(mu)
     xyz = np.stack((r * np.sin(thetas) * np.cos(phis), r * np.sin(thetas) * np.sin(phis),
                     r * np.cos(thetas)), axis=1).astype(np.float32)
-    if exact_knn and P <= 200_000:
+    if exact_knn and P >= 4:
         from scipy.spatial import cKDTree
-        d, _ = cKDTree(xyz).query(xyz, k=4)
+        d, _ = cKDTree(xyz).query(xyz, k=4, workers=-1)
         dist2 = (d[:, 1:] ** 2).mean(1)
     else:
         # expected k-th NN distance in a uniform density n: r_k^3 ~ k / (4/3 pi n)

@@ -15,9 +15,14 @@
  *
  * Conventions
  *   - every pointer is a DEVICE pointer owned by the caller unless stated otherwise;
- *     the library never allocates or frees device memory and keeps no global mutable state
- *     (other than a thread-local error string);
- *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no host sync;
+ *     the library never allocates or frees device memory.  Process-wide state it does keep:
+ *     a thread-local error string; per device, one lazily created non-blocking side stream +
+ *     two events (lets the two tile-sort size classes overlap; creation is mutex-guarded, calls
+ *     on DIFFERENT streams of one device from different host threads must still be serialised by
+ *     the caller because they share those events); per kernel, a "shared-memory attribute set"
+ *     bit per device; and the optional b200gsr_profile_* event store (not thread-safe);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*) of the CURRENT device;
+ *     no host sync, no memset nodes on the main path (capturable into a CUDA graph);
  *   - return value: 0 = OK, negative = error (see b200gsr_last_error());
  *   - tensors are dense, row-major fp32 unless stated; layouts follow the reference call sites:
  *       means3D[P,3] means2D-grad[P,3] shs[P,M,3] colors_precomp[P,3] opacities[P,1]
@@ -36,7 +41,7 @@
 extern "C" {
 #endif
 
-#define B200GSR_VERSION 1
+#define B200GSR_VERSION 2
 
 /* error codes */
 #define B200GSR_OK 0
@@ -65,13 +70,18 @@ typedef struct b200gsr_params {
 
 /* Byte offsets of the arrays inside the `saved` buffer (for tests / debugging / backward). */
 typedef struct b200gsr_saved_layout {
-    size_t header;        /* uint32[8]: [0]=num_pairs (true D, may exceed max_pairs) [1]=max_pairs
-                             [2]=num_tiles [3]=overflow flag [4]=num_big_tiles [5..7] reserved */
+    size_t header;        /* uint32[32]: [0]=num_pairs (true D, may exceed max_pairs) [1]=max_pairs
+                             [2]=num_tiles [3]=overflow flag [4]=num_big_tiles [5]=non-empty tiles
+                             [8..15]=backward work-queue counters (zero between calls) rest reserved */
     size_t tile_start;    /* uint32[num_tiles+1] exclusive prefix of per-tile pair counts */
     size_t work_order;    /* uint32[num_tiles] tile ids, longest list first */
     size_t n_contrib;     /* uint32[H*W] index(1-based) of the last blended entry per pixel */
     size_t keys;          /* uint64[max_pairs+2] (depth_bits<<32 | gaussian idx), tile-major, depth-sorted */
     size_t geom;          /* 48-byte per-Gaussian records [P] (see common.cuh), gathered by the composite kernels */
+    size_t dgeom;         /* float[P*12] screen-space gradient accumulators of the backward.  Rows of visible
+                             Gaussians are zeroed by the forward and restored to zero by the backward
+                             (read-and-clear), so no memset is ever needed.  Absent (size 0) when the
+                             layout is queried with with_backward = 0 */
     size_t total;
 } b200gsr_saved_layout;
 
@@ -82,17 +92,21 @@ typedef struct b200gsr_scratch_layout {
     size_t tile_cursor;   /* uint32[16][num_tiles] write cursors */
     size_t rectdepth;     /* uint4[P]: (minx|miny<<16, maxx|maxy<<16, depth bits, tiles touched) */
     size_t ms_hist;       /* uint32[ceil(P/4096)][num_tiles] per-CTA tile histograms (multisplit binning) */
-    size_t dgeom;         /* backward only: float[P*12] screen-space gradient accumulators */
     size_t total;
 } b200gsr_scratch_layout;
 
 int b200gsr_version(void);
 const char* b200gsr_last_error(void);
 
+/* forward flags */
+#define B200GSR_FWD_NO_BACKWARD 1u   /* `saved` was sized with with_backward = 0: skip the gradient accumulators */
+
 /* Sizes/offsets of the two caller-owned buffers.  `saved` must stay alive until backward;
- * `scratch` is transient.  max_pairs = capacity for (tile,Gaussian) pairs ("num_rendered"). */
+ * `scratch` is transient (forward only).  max_pairs = capacity for (tile,Gaussian) pairs
+ * ("num_rendered").  with_backward = 0 drops the 48 B/Gaussian accumulator array (inference,
+ * important_score renders). */
 int b200gsr_saved_layout_query(int32_t P, int32_t H, int32_t W, uint64_t max_pairs,
-                               b200gsr_saved_layout* out);
+                               int32_t with_backward, b200gsr_saved_layout* out);
 int b200gsr_scratch_layout_query(int32_t P, int32_t H, int32_t W, uint64_t max_pairs,
                                  b200gsr_scratch_layout* out);
 
@@ -113,7 +127,8 @@ int b200gsr_forward(const b200gsr_params* prm,
                     const float* cov3D_precomp,
                     float* out_color, float* out_depth_alpha, int32_t* radii, float* score,
                     void* scratch, size_t scratch_bytes, void* saved, size_t saved_bytes,
-                    uint64_t max_pairs, uint32_t* host_notify, uint32_t notify_seq, void* stream);
+                    uint64_t max_pairs, uint32_t flags, uint32_t* host_notify, uint32_t notify_seq,
+                    void* stream);
 
 /*
  * Backward (replaces _C.rasterize_gaussians_backward).  Inputs as in forward plus the forward's
@@ -121,7 +136,9 @@ int b200gsr_forward(const b200gsr_params* prm,
  * gradients dL/dcolor[3,H,W], dL/ddepth_alpha[2,H,W].  Outputs are fully overwritten (zeros for
  * culled Gaussians): d_means3D[P,3], d_means2D[P,3] (NDC-scaled screen-space gradient, z=0),
  * d_opacities[P,1], and d_shs[P,M,3] | d_colors[P,3], (d_scales[P,3], d_rotations[P,4]) |
- * d_cov3D[P,6] matching the forward's input choice.
+ * d_cov3D[P,6] matching the forward's input choice.  The call mutates and restores the
+ * accumulators inside `saved` (hence non-const): the same `saved` may be back-propagated again
+ * (retain_graph).  `scratch` is unused since version 2 (may be NULL / 0).
  */
 int b200gsr_backward(const b200gsr_params* prm,
                      const float* means3D, const float* shs, const float* colors_precomp,
@@ -129,7 +146,7 @@ int b200gsr_backward(const b200gsr_params* prm,
                      const float* cov3D_precomp,
                      const int32_t* radii, const float* out_depth_alpha,
                      const float* dL_dcolor, const float* dL_ddepth_alpha,
-                     const void* saved, size_t saved_bytes, void* scratch, size_t scratch_bytes,
+                     void* saved, size_t saved_bytes, void* scratch, size_t scratch_bytes,
                      uint64_t max_pairs,
                      float* d_means3D, float* d_means2D, float* d_shs, float* d_colors,
                      float* d_opacities, float* d_scales, float* d_rotations, float* d_cov3D,

@@ -18,9 +18,10 @@ def distCUDA2(points: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     nbytes = int(lib.b200gsr_dist2_scratch_bytes(P))
     scratch = torch.empty(nbytes, dtype=torch.uint8, device=pts.device)
-    rc = lib.b200gsr_dist2_knn3(P, C.c_void_p(pts.data_ptr()), C.c_void_p(out.data_ptr()),
-                                C.c_void_p(scratch.data_ptr()), nbytes,
-                                C.c_void_p(torch.cuda.current_stream(pts.device).cuda_stream))
+    with torch.cuda.device(pts.device):     # the library launches on the CURRENT device
+        rc = lib.b200gsr_dist2_knn3(P, C.c_void_p(pts.data_ptr()), C.c_void_p(out.data_ptr()),
+                                    C.c_void_p(scratch.data_ptr()), nbytes,
+                                    C.c_void_p(torch.cuda.current_stream(pts.device).cuda_stream))
     if rc:
         raise RuntimeError(f"b200gsr_dist2_knn3 failed ({rc}): {_lib.last_error()}")
     return out

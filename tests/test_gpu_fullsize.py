@@ -15,7 +15,7 @@ P, H, W = 1_000_000, 1024, 1024
 
 @pytest.fixture(scope="module")
 def big():
-    sc, cam, deg = U.make_inputs(P, H, W, seed=0, exact_knn=False)
+    sc, cam, deg = U.make_inputs(P, H, W, seed=0)     # the bench workload (exact 3-NN scales)
     dev = torch.device("cuda", torch.cuda.current_device())
     t = {k: v.to(dev) for k, v in sc.items()}
     return sc, cam, deg, t, dev
@@ -122,29 +122,32 @@ def _arbitrate_radii(sc, cam, cuda_radii, oracle_radii):
 
 
 def test_sampled_tiles_match_the_oracle_at_full_size(big):
+    """cfg3: complete sorted list bit-exact; forward on 24 list-length-stratified tiles within the
+    measured budgets; COMPLETE parameter gradients vs the fp64 oracle with the incoming gradients
+    masked to those tiles (long lists: fp32 atomic accumulation over thousands of contributors,
+    rcp.approx drift over hundreds of back-to-front steps, the ring wrap)."""
+    from tests import parity_budgets as B
+    from tests import parity_tools as PT
     sc, cam, deg, t, dev = big
     color, radii, da, st = _forward(t, cam, deg, dev)
-    S = U.oracle_settings(cam, deg)
-    with torch.no_grad():
-        pre = O.preprocess(S, sc["means3D"], sc["opacities"], shs=sc["shs"], scales=sc["scales"],
-                           rotations=sc["rotations"])
-        keys, pl, ranges = O.bin_and_sort(pre, S)
+    S, pre, keys, pl, ranges, odec = PT.oracle_lists(sc, cam, deg)
     _arbitrate_radii(sc, cam, radii.cpu().numpy(), pre["radii"].numpy())
     dec = U.decode_saved(st.saved, P, H, W, st.capacity)
     assert dec["num_pairs"] == len(pl)
-    np.testing.assert_array_equal(dec["idx"], pl)                      # the full 6.4M-entry sorted list
+    np.testing.assert_array_equal(dec["idx"], pl)                      # the full multi-million-entry sorted list
     np.testing.assert_array_equal(dec["tile_start"][:-1], ranges[:, 0])
-    n = ranges[:, 1] - ranges[:, 0]
-    order = np.argsort(-n, kind="stable")
-    nonempty = int((n > 0).sum())
-    tiles = [int(x) for x in order[:nonempty:max(nonempty // 12, 1)]][:12]
+    tiles = PT.sample_tiles(ranges, 24)
+    mask = PT.tile_mask(tiles, H, W)
     with torch.no_grad():
-        oc, oda, _, _ = O.composite(pre, pl, ranges, S, tiles=tiles)
-    gx = W // 16
-    for tile in tiles:
-        ty, tx = divmod(tile, gx)
-        sl = (slice(None), slice(ty * 16, ty * 16 + 16), slice(tx * 16, tx * 16 + 16))
-        dc = (color[sl].cpu() - oc[sl]).abs()
-        dd = (da[sl].cpu() - oda[sl]).abs()
-        assert (dc > 1e-4).float().mean() <= 2e-3 and dc.max() < 6e-3, tile
-        assert (dd > 1e-4).float().mean() <= 2e-3 and dd.max() < 3e-2, tile
+        oc, oda, onc, _ = O.composite(pre, pl, ranges, S, tiles=tiles)
+    stats = PT.forward_stats(color, da, oc, oda, cu_nc=dec["n_contrib"], ref_nc=onc.numpy(), mask=mask)
+    B.check_forward("cfg3_1M_1024", stats)
+    # backward: gradients flow only into the sampled tiles, the parameter gradient is compared in full
+    g = torch.Generator().manual_seed(13)
+    gc = torch.randn(3, H, W, generator=g) / (H * W) * mask
+    gd = torch.randn(2, H, W, generator=g) / (H * W) * mask
+    want = PT.oracle_backward_on_tiles(sc, cam, deg, tiles, gc, gd, odec, group=3)
+    got = PT.cuda_forward_backward(sc, cam, deg, gc, gd, device=dev)
+    errs = PT.grad_errors(got["grads"], want)
+    for k in ("means3D", "scales", "rotations", "opacities", "shs", "means2D"):
+        assert errs[k]["rel_l2"] < B.BWD_REL, (k, errs[k])

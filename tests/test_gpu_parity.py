@@ -224,8 +224,16 @@ def test_long_tile_lists_exercise_both_sort_paths_and_overflow_retry():
     sc, cam, deg = U.make_inputs(P, H, W, seed=17, radius=0.3, cam_radius=6.0, exact_knn=False, scale_mul=0.5)
     ref = run_oracle(sc, cam, deg)
     assert (ref["ranges"][:, 1] - ref["ranges"][:, 0]).max() > 16384
+    dstate = R._device_state(torch.device("cuda", torch.cuda.current_device()))
+    old = (R._pair_mode, R._MIN_CAPACITY, R._MIN_PAIRS_PER_GAUSSIAN, dstate.capacity, dstate.user_capacity)
+    R.flush_checks()
+    R.set_pair_count_mode("sync")
+    R._MIN_CAPACITY, R._MIN_PAIRS_PER_GAUSSIAN = 1024, 0
     R.set_workspace_capacity(1024)
-    cu = run_cuda(sc, cam, deg)
+    try:
+        cu = run_cuda(sc, cam, deg)
+    finally:
+        R._pair_mode, R._MIN_CAPACITY, R._MIN_PAIRS_PER_GAUSSIAN, dstate.capacity, dstate.user_capacity = old
     np.testing.assert_array_equal(cu["radii"].cpu().numpy(), ref["radii"].numpy())
     check_lists(sc, cam, ref)
     check_images(cu, ref)

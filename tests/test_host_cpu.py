@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert set(_lib.EXPORTS) == set(syms)
     for s in syms:
         assert hasattr(lib, s), s
-    assert lib.b200gsr_version() == 1
+    assert lib.b200gsr_version() == 2
 
 
 def test_layout_queries_are_monotone_and_aligned():
@@ -32,9 +32,11 @@ def test_layout_queries_are_monotone_and_aligned():
     b = _lib.saved_layout(1000, 256, 256, 1 << 21)
     assert b.total > a.total and a.keys % 256 == 0 and a.geom % 256 == 0 and a.n_contrib % 256 == 0
     assert b.total - a.total == (1 << 20) * 8          # capacity only scales the 8-byte key list
-    assert a.total - a.geom >= 1000 * 48
+    assert a.dgeom - a.geom >= 1000 * 48 and a.total - a.dgeom >= 1000 * 48
+    nb = _lib.saved_layout(1000, 256, 256, 1 << 20, with_backward=False)
+    assert nb.dgeom == a.dgeom and nb.total == nb.dgeom       # inference layout drops the accumulators
     s = _lib.scratch_layout(1000, 256, 256, 1 << 20)
-    assert s.counters == 0 and s.tile_count < s.tile_cursor < s.rectdepth < s.dgeom < s.total
+    assert s.counters == 0 and s.tile_count < s.tile_cursor < s.rectdepth < s.ms_hist <= s.total
     with pytest.raises(RuntimeError):
         _lib.saved_layout(10, 16, 16, 1 << 33)
 
@@ -43,7 +45,7 @@ def test_forward_rejects_bad_arguments_without_a_gpu():
     from dreamscene_b200 import _lib
     lib = _lib.load()
     prm = _lib.Params(4, 16, 3, 32, 32, 0.3, 0.3, 1.0, 0, 0, 0, 0, 0, 0)
-    rc = lib.b200gsr_forward(C.byref(prm), *([None] * 11), None, 0, None, 0, 1024, None, 0, None)
+    rc = lib.b200gsr_forward(C.byref(prm), *([None] * 11), None, 0, None, 0, 1024, 0, None, 0, None)
     assert rc == -1 and "device pointers" in _lib.last_error()
 
 
@@ -90,3 +92,39 @@ def test_gradient_sections_are_256_byte_aligned_for_any_point_count():
                 assert offs[a] % 64 == 0                               # 64 floats = 256 bytes
                 end = offs[b] if b else total
                 assert end - offs[a] >= P * widths[a]                  # sections never overlap
+
+
+def test_pair_count_mode_switch_and_capacity_policy():
+    from dreamscene_b200 import rasterizer as R
+    assert R._pair_mode in ("sync", "async")
+    old = R._pair_mode
+    try:
+        R.set_pair_count_mode("sync"); assert R._pair_mode == "sync"
+        R.set_pair_count_mode("async"); assert R._pair_mode == "async"
+        with pytest.raises(ValueError):
+            R.set_pair_count_mode("maybe")
+    finally:
+        R.set_pair_count_mode(old)
+    assert R._round_cap(1) == R._MIN_CAPACITY and R._round_cap((1 << 20) + 1) % (1 << 18) == 0
+
+
+def test_deferred_overflow_check_reads_the_notify_ring_without_blocking():
+    """The async pair-count protocol on the host side, with the device's writes faked."""
+    import numpy as np
+    from dreamscene_b200 import rasterizer as R
+    d = R._Device(torch.device("cuda", 0))
+    d.notify = torch.zeros(R._NOTIFY_SLOTS, 4, dtype=torch.int32)     # unpinned stand-in
+    d.notify_np = d.notify.numpy()
+    d.free_slots = list(range(R._NOTIFY_SLOTS - 1, -1, -1))
+    s1, s2 = d.free_slots.pop(), d.free_slots.pop()
+    d.pending = [(s1, 11, 1 << 20), (s2, 12, 1 << 20)]
+    R._resolve_pending(d)                       # nothing reported yet: stays pending, no wait
+    assert len(d.pending) == 2
+    d.notify_np[s1] = (11, 500_000, 0, 64)      # first forward reports 0.5M pairs
+    R._resolve_pending(d)
+    assert d.pending == [(s2, 12, 1 << 20)] and d.last_pairs == 500_000 and s1 in d.free_slots
+    assert d.capacity == R._round_cap(1_000_000)
+    d.notify_np[s2] = (12, 3 << 20, 1, 64)      # second one overflowed its 1M-pair buffer
+    with pytest.raises(R.PairCapacityOverflow):
+        R._resolve_pending(d)
+    assert not d.pending and d.capacity >= 6 << 20      # raised so that a retry fits

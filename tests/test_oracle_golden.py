@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 from oracle import splat_ref as O
-from dreamscene_b200 import cameras
+from harness import cameras
 
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_pins.npz"))
 

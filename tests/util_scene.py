@@ -5,13 +5,13 @@ import numpy as np
 import torch
 
 from oracle import splat_ref as O
-from dreamscene_b200 import cameras, synthetic
+from harness import cameras, synthetic
 
 
 def make_inputs(P, H, W, seed=0, sh_max=3, sh_degree=None, radius=0.5, phi=0.0, fovx=0.55,
                 opacity="sigmoid_normal", cam_radius=3.5, exact_knn=None, scale_mul=1.0):
     sc = synthetic.ball_scene(P, radius=radius, sh_degree_max=sh_max, seed=seed, opacity=opacity,
-                              exact_knn=(P <= 50000) if exact_knn is None else exact_knn)
+                              exact_knn=True if exact_knn is None else exact_knn)
     sc["scales"] = sc["scales"] * scale_mul
     cam = cameras.orbit_camera(radius=cam_radius, phi_deg=phi, fovx=fovx, height=H, width=W)
     deg = sh_max if sh_degree is None else sh_degree

@@ -1,0 +1,146 @@
+#!/usr/bin/env python
+"""Measure (not assert) the CUDA-vs-oracle parity statistics on BASELINE.json's configurations and
+write them as JSON (committed as profiles/r02_parity_stats.json; tests/parity_budgets.py is set from it).
+
+  python tools/parity_stats.py --out gpurun_out/r02_parity_stats.json            # both variants
+  python tools/parity_stats.py --variant exact --configs cfg1_10k_256            # one variant, one config
+
+Per config and per build variant ("default" = ex2.approx on a log2e-scaled conic + rcp.approx;
+"exact" = libb200gsr_exact.so: expf, IEEE division, oracle operation order in the exponent):
+  forward  - outlier count / fraction / max |diff| for colour, depth, T; n_contrib mismatch rate
+             (whole frame for cfg1/cfg2, list-length-stratified tile sample for cfg3)
+  backward - norm-wise relative error of all six gradients vs the fp64 oracle evaluated on the fp32 pair
+             lists (whole frame for cfg1; incoming gradients masked to the sampled tiles otherwise)
+  timing   - fwd+bwd ms/step of the variant at that config (CUDA events), i.e. what the approximation buys
+Test infrastructure: imports oracle/ as the checker only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    "cfg1_10k_256": dict(P=10_000, H=256, W=256, tiles=None),
+    "cfg2_100k_512": dict(P=100_000, H=512, W=512, tiles=32),
+    "cfg2b_81920_512": dict(P=81_920, H=512, W=512, tiles=32),
+    "cfg3_1M_1024": dict(P=1_000_000, H=1024, W=1024, tiles=48),
+}
+
+
+def run_variant(variant, configs, quick):
+    import numpy as np
+    import torch
+    from dreamscene_b200 import _lib
+    from oracle import splat_ref as O
+    from tests import parity_tools as PT
+    from tests import util_scene as U
+    from tests.test_gpu_parity import run_oracle
+    from dreamscene_b200 import rasterizer as R
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    out = {"lib": os.path.basename(_lib.LIB_PATH)}
+    for name in configs:
+        cfg = CONFIGS[name]
+        P, H, W = cfg["P"], cfg["H"], cfg["W"]
+        t0 = time.time()
+        sc, cam, deg = U.make_inputs(P, H, W)
+        S, pre, keys, pl, ranges, dec = PT.oracle_lists(sc, cam, deg)
+        res = {"P": P, "H": H, "W": W, "tile_pairs": int(len(pl)), "visible": int(pre["visible"].sum())}
+        full = cfg["tiles"] is None
+        ntile = cfg["tiles"] if not quick or full else max(8, cfg["tiles"] // 4)
+        tiles = None if full else PT.sample_tiles(ranges, ntile)
+        mask = None if full else PT.tile_mask(tiles, H, W)
+        with torch.no_grad():
+            oc, oda, onc, _ = O.composite(pre, pl, ranges, S, tiles=tiles)
+        g = torch.Generator().manual_seed(17)
+        gc = torch.randn(3, H, W, generator=g) / (H * W)
+        gd = torch.randn(2, H, W, generator=g) / (H * W)
+        if mask is not None:
+            gc, gd = gc * mask, gd * mask
+        # CUDA
+        cu = PT.cuda_forward_backward(sc, cam, deg, gc, gd, device=dev)
+        tt = {k: v.to(dev) for k, v in sc.items()}
+        with torch.no_grad():
+            _, radii, _, _, st = R._forward_impl(U.cuda_settings(cam, deg, device=dev), tt["means3D"], tt["shs"], None,
+                                                 tt["opacities"], tt["scales"], tt["rotations"], None, with_backward=False)
+        torch.cuda.synchronize()
+        d = U.decode_saved(st.saved, P, H, W, st.capacity)
+        res["lists_bit_exact"] = bool(d["num_pairs"] == len(pl) and np.array_equal(d["idx"], pl)
+                                      and np.array_equal(d["tile_start"][:-1], ranges[:, 0])
+                                      and np.array_equal(radii.cpu().numpy(), pre["radii"].numpy()))
+        res["forward"] = PT.forward_stats(cu["color"], cu["depth_alpha"], oc, oda, cu_nc=d["n_contrib"],
+                                          ref_nc=onc.numpy(), mask=mask)
+        res["forward"]["compared"] = "whole frame" if full else f"{len(tiles)} tiles sampled evenly over the non-empty tiles ordered by list length"
+        # oracle backward (fp64 on the fp32 lists)
+        tl = list(range(len(ranges))) if full else tiles
+        tl = [t for t in tl if ranges[t, 1] > ranges[t, 0]]
+        want = PT.oracle_backward_on_tiles(sc, cam, deg, tl, gc, gd, dec, group=16 if P <= 100_000 else 3)
+        res["backward"] = PT.grad_errors(cu["grads"], want)
+        res["backward"]["compared"] = "whole frame" if full else "complete parameter gradients, incoming gradients masked to the sampled tiles"
+        # timing of this variant
+        from dreamscene_b200 import GaussianRasterizer
+        prm = {k: v.to(dev).requires_grad_(True) for k, v in sc.items()}
+        m2d = torch.zeros(P, 3, device=dev, requires_grad=True)
+        Sg = U.cuda_settings(cam, deg, device=dev)
+        gcd, gdd = gc.to(dev), gd.to(dev)
+
+        def step():
+            for v in prm.values():
+                v.grad = None
+            c, r, a = GaussianRasterizer(Sg)(means3D=prm["means3D"], means2D=m2d, opacities=prm["opacities"],
+                                             shs=prm["shs"], scales=prm["scales"], rotations=prm["rotations"])
+            torch.autograd.backward([c, a], [gcd, gdd])
+        for _ in range(5):
+            step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        n = 20
+        for _ in range(n):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        res["fwd_bwd_ms"] = e0.elapsed_time(e1) / n
+        res["wall_s"] = time.time() - t0
+        out[name] = res
+        print(f"[{variant}] {name}: {json.dumps(res['forward'])[:300]} ... {res['fwd_bwd_ms']:.3f} ms", file=sys.stderr, flush=True)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "r02_parity_stats.json"))
+    ap.add_argument("--variant", default=None, choices=["default", "exact"])
+    ap.add_argument("--configs", default=",".join(CONFIGS))
+    ap.add_argument("--quick", action="store_true")
+    a = ap.parse_args()
+    configs = [c for c in a.configs.split(",") if c]
+    if a.variant is not None:       # child: one variant, JSON on stdout
+        print(json.dumps(run_variant(a.variant, configs, a.quick)))
+        return
+    from dreamscene_b200 import _build
+    result = {"note": "CUDA vs oracle/splat_ref.py; |diff| > 1e-4 counts as an outlier (north_star forward tolerance); "
+                      "oracle parity itself is pinned only for SH/cov3D/cameras (DESIGN.md)"}
+    for variant in ("default", "exact"):
+        lib = _build.build(variant=variant)
+        env = dict(os.environ, B200GSR_LIB=lib)
+        cmd = [sys.executable, os.path.abspath(__file__), "--variant", variant, "--configs", ",".join(configs)]
+        if a.quick:
+            cmd.append("--quick")
+        r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, text=True)
+        if r.returncode != 0:
+            result[variant] = {"error": f"exit {r.returncode}"}
+            continue
+        result[variant] = json.loads(r.stdout.strip().splitlines()[-1])
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    json.dump(result, open(a.out, "w"), indent=1)
+    print(a.out)
+
+
+if __name__ == "__main__":
+    main()
