@@ -88,7 +88,7 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", "200"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -226,11 +226,32 @@ def run_reference(args, wl_name, wl, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(wl_name, wl, world):
+def workload_config(wl_name, wl, world, sh_degree=3):
     """The `config` object both arms print (identical keys, so the driver sees the same config)."""
-    return {"workload": wl_name, "P": wl["P"], "H": wl["H"], "W": wl["W"], "sh_degree": 3, "M": 16,
+    return {"workload": wl_name, "P": wl["P"], "H": wl["H"], "W": wl["W"], "sh_degree": sh_degree, "M": 16,
             "views_per_step": world, "parallelism": f"view-sharded dp{world}",
             "scales": "exact 3-NN (reference recipe)" if wl.get("exact_knn", True) else "analytic 3-NN stand-in (round-1 workload)"}
+
+
+def secondary_roofline(evals, mean_ms, clk):
+    """SURVEY 8(d) secondary roofline: what actually bounds the composite kernels once records sit in
+    shared memory is the rate of (pixel, Gaussian) evaluations (each warp-level pair = 32 of them,
+    ~20 fp32 ops + 1 MUFU.EX2 in the forward, ~60 + 2 MUFU in the backward), against the SM's issue
+    peaks at the measured clock: 4 warp-instructions/clk/SM issue, 16 MUFU lanes/clk/SM."""
+    mhz = (clk or {}).get("sm_mhz") or 1965.0
+    sms = 148
+    issue_peak = sms * 4 * mhz * 1e6                    # warp instructions / s
+    mufu_peak = sms * 16 * mhz * 1e6                    # lane-level ex2/rcp per s
+    out = {"unit": "pixel-pair evaluations/s", "sm_mhz": mhz, "counts": evals,
+           "mufu_peak_lanes_per_s": mufu_peak, "issue_peak_warp_instr_per_s": issue_peak}
+    for name, key, mufu_per_eval in (("composite_fwd", "fwd_pairs_evaluated", 1), ("composite_bwd", "bwd_pairs_evaluated", 1)):
+        t = mean_ms.get(name)
+        n = evals.get(key, 0)
+        if t and n:
+            rate = 32.0 * n / (t * 1e-3)
+            out[name] = {"evals_per_s": rate, "frac_of_mufu_peak": rate * mufu_per_eval / mufu_peak,
+                         "issue_slots_per_warp_pair": issue_peak * t * 1e-3 / n}
+    return out
 
 
 def algorithmic_bytes(P, V, D, N, M):
@@ -254,6 +275,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3_1M_1024", choices=sorted(WORKLOADS))
+    ap.add_argument("--sh-degree", type=int, default=3, help="active SH degree (the metric's config is 3)")
+    ap.add_argument("--reduce", default="backward", choices=["backward", "deferred"],
+                    help="N>1: chunk-overlapped all-reduce inside the rasterizer backward, or DDP-style "
+                         "all-reduce of the leaf gradients after it (dreamscene_b200.parallel)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -274,7 +299,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        parallel.enable_view_sharding()
+        parallel.enable_view_sharding(mode=args.reduce)
     _lib.load()
 
     sc, cam, gc_h, gd_h = make_scene(wl, rank)
@@ -286,7 +311,7 @@ def main():
     S = GaussianRasterizationSettings(
         image_height=H, image_width=W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
         bg=torch.ones(3, device=dev), scale_modifier=1.0, viewmatrix=cam.world_view_transform.to(dev),
-        projmatrix=cam.full_proj_transform.to(dev), sh_degree=3, campos=cam.camera_center.to(dev),
+        projmatrix=cam.full_proj_transform.to(dev), sh_degree=args.sh_degree, campos=cam.camera_center.to(dev),
         prefiltered=False, score_flag=False)
     rast = GaussianRasterizer(S)
     m2d = torch.zeros(P, 3, device=dev, requires_grad=True)
@@ -298,6 +323,8 @@ def main():
         color, radii, da = rast(means3D=p["means3D"], means2D=m2d, opacities=p["opacities"], shs=p["shs"],
                                 scales=p["scales"], rotations=p["rotations"])
         torch.autograd.backward([color, da], [gc, gd])
+        if world > 1 and args.reduce == "deferred":
+            parallel.all_reduce_gradients(list(p.values()), active_columns={p["shs"]: (args.sh_degree + 1) ** 2})
         return color, radii, da
 
     def barrier():
@@ -305,18 +332,31 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # nvidia-smi takes a driver-wide lock for tens of ms while it initialises: start the sampler
+    # BEFORE the warm-up so that stall never lands inside the timed region (it did in the first
+    # round-2 run: one 76 ms step)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(1.0)
     for _ in range(args.warmup):
         _, radii, _ = step(prm)
     barrier()
     V = int((radii > 0).sum())
     D = int(R.last_pair_count(dev))
 
+    # pair-evaluation counts for the secondary roofline: ONE extra, untimed step with the
+    # instrumented kernel instantiations
+    counters = torch.zeros(16, dtype=torch.int64, device=dev)
+    _lib.debug_counters(counters.data_ptr())
+    step(prm)
+    torch.cuda.synchronize(dev)
+    _lib.debug_counters(None)
+    evals = dict(zip(_lib.STAT_NAMES, [int(x) for x in counters.tolist()]))
+    evals.pop("_9", None)
+
     # ---- timed region 1: device-resident inputs --------------------------------------------
     _lib.profile_enable(args.steps)
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-        time.sleep(0.3)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]   # per-step spread only
     barrier()
@@ -345,6 +385,7 @@ def main():
         step(prm)
         reduced = torch.cat([prm[k].grad.reshape(-1) for k in names]).clone()
         parallel.disable_view_sharding()
+        reduce_mode, args.reduce = args.reduce, "none"
         total = torch.zeros_like(reduced)
         for v in range(world):
             sc_v, cam_v, gc_v, gd_v = make_scene(wl, v) if v != rank else (sc, cam, gc_h, gd_h)
@@ -356,7 +397,8 @@ def main():
                                                 shs=prm["shs"], scales=prm["scales"], rotations=prm["rotations"])
             torch.autograd.backward([c_, a_], [gc_v.to(dev), gd_v.to(dev)])
             total += torch.cat([prm[k].grad.reshape(-1) for k in names])
-        parallel.enable_view_sharding()
+        args.reduce = reduce_mode
+        parallel.enable_view_sharding(mode=args.reduce)
         err = ((reduced - total).double().norm() / total.double().norm().clamp_min(1e-300)).reshape(1)
         dist.all_reduce(err, op=dist.ReduceOp.MAX)
         grad_check = {"rel_err_max_over_ranks": float(err.item()), "views_summed": world,
@@ -432,14 +474,15 @@ def main():
             "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(wl_name, wl, world),
+            "config": workload_config(wl_name, wl, world, args.sh_degree),
             "workload_stats": {"visible": V, "tile_pairs": D,
                                "l2": "inputs larger than L2 (params 236 MB read + 248 MB grads written + %d MB keys per step)" % (D * 8 // 2**20)},
             "ms_per_step_spread": {"median": float(np.median(per_step)), "min": float(per_step.min()),
                                    "max": float(per_step.max())},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": mean_ms[dom]},
+                         "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": mean_ms[dom],
+                         "secondary": secondary_roofline(evals, mean_ms, clk)},
             "step_hbm": {"algorithmic_bytes": step_alg, "achieved_gbs": step_alg / (ms_step * 1e-3) / 1e9,
                          "frac": step_alg / (ms_step * 1e-3) / 1e9 / peak},
             "stages_ms": mean_ms,
@@ -450,7 +493,13 @@ def main():
             line["e2e"] = e2e
         if grad_check:
             line["grad_check"] = grad_check
-            line["limiting_collective"] = "ncclAllReduce(SUM, fp32) of the flat parameter-gradient buffer, issued inside backward"
+            ncoef = (args.sh_degree + 1) ** 2
+            floats = 3 + 1 + 3 * ncoef + 3 + 4
+            line["limiting_collective"] = (
+                f"ncclAllReduce(SUM, fp32) of the parameter gradients: {floats} floats/Gaussian = {floats * 4 * P / 1e6:.0f} MB/step "
+                + ("in 8 coalesced chunks overlapped with project_bwd (inside backward)" if args.reduce == "backward"
+                   else "in one coalesced call on the leaf gradients after backward (DDP-style)"))
+            line["reduce_mode"] = args.reduce
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_dict(wl, cpu_oracle_step(wl, 0))
         print(json.dumps(line), flush=True)

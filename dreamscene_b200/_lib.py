@@ -9,9 +9,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200GSR_LIB", os.path.join(HERE, "libb200gsr.so"))   # override: A/B builds only
 
 EXPORTS = ["b200gsr_version", "b200gsr_last_error", "b200gsr_saved_layout_query",
-           "b200gsr_scratch_layout_query", "b200gsr_forward", "b200gsr_backward",
+           "b200gsr_scratch_layout_query", "b200gsr_forward", "b200gsr_backward", "b200gsr_backward_ex",
            "b200gsr_mark_visible", "b200gsr_profile_enable", "b200gsr_profile_counts",
-           "b200gsr_profile_read", "b200gsr_dist2_scratch_bytes", "b200gsr_dist2_knn3"]
+           "b200gsr_profile_read", "b200gsr_debug_counters", "b200gsr_dist2_scratch_bytes", "b200gsr_dist2_knn3"]
 
 
 class Params(C.Structure):
@@ -36,6 +36,7 @@ class ScratchLayout(C.Structure):
 _lib = None
 ABI_VERSION = 2
 FWD_NO_BACKWARD = 1
+BWD_COMPOSITE, BWD_PROJECT = 1, 2
 
 
 def load():
@@ -65,11 +66,15 @@ def load():
         [vp, sz, vp, sz, u64, u32, vp, u32, vp]
     lib.b200gsr_backward.argtypes = [C.POINTER(Params)] + [vp] * 7 + [vp] * 4 + \
         [vp, sz, vp, sz, u64] + [vp] * 8 + [vp]
+    lib.b200gsr_backward_ex.argtypes = lib.b200gsr_backward.argtypes[:-1] + [u32, i32, i32, i32, vp]
+    lib.b200gsr_backward_ex.restype = C.c_int
     lib.b200gsr_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]
     lib.b200gsr_dist2_scratch_bytes.argtypes = [i32]
     lib.b200gsr_dist2_scratch_bytes.restype = C.c_size_t
     lib.b200gsr_dist2_knn3.argtypes = [i32, vp, vp, vp, sz, vp]
     lib.b200gsr_dist2_knn3.restype = C.c_int
+    lib.b200gsr_debug_counters.argtypes = [vp]
+    lib.b200gsr_debug_counters.restype = C.c_int
     lib.b200gsr_profile_enable.argtypes = [i32]
     lib.b200gsr_profile_counts.argtypes = [C.POINTER(i32), C.POINTER(i32)]
     lib.b200gsr_profile_read.argtypes = [i32, i32, C.POINTER(C.c_float)]
@@ -133,3 +138,14 @@ def profile_collect() -> dict:
         for k, name in enumerate(BWD_STAGES):
             out[name].append(float(buf[k]))
     return out
+
+
+STAT_NAMES = ("bwd_pairs_evaluated", "bwd_pairs_contributing", "bwd_lane_contributions", "bwd_k1", "bwd_k2",
+              "bwd_k3_4", "bwd_k5_8", "bwd_k9_16", "bwd_k17_32", "_9", "fwd_pairs_evaluated", "fwd_lane_blends")
+
+
+def debug_counters(ptr) -> None:
+    """ptr: device pointer to 16 zeroed uint64 (or None to switch the instrumented kernels off)."""
+    rc = load().b200gsr_debug_counters(C.c_void_p(ptr) if ptr else None)
+    if rc:
+        raise RuntimeError(last_error())

@@ -61,6 +61,7 @@ struct DeviceState {
     cudaEvent_t fork = nullptr, join = nullptr;
 };
 DeviceState g_dev[64];
+unsigned long long* g_stats = nullptr;   // b200gsr_debug_counters (process-wide, diagnostics only)
 std::mutex g_dev_mutex;
 
 // Returns nullptr only if the device ordinal is out of range or CUDA itself fails.
@@ -190,7 +191,7 @@ int b200gsr_forward(const b200gsr_params* prm, const float* means3D, const float
     a.scratch = static_cast<uint8_t*>(scratch); a.saved = static_cast<uint8_t*>(saved);
     a.max_pairs = (uint32_t)max_pairs;
     a.host_notify = host_notify; a.notify_seq = notify_seq;
-    a.flags = flags; a.num_sms = ds->num_sms;
+    a.flags = flags; a.num_sms = ds->num_sms; a.stats = g_stats;
     a.stream = static_cast<cudaStream_t>(stream);
 
     // The queue counters and the per-tile pair counters (contiguous at the start of scratch) must be
@@ -236,17 +237,22 @@ int b200gsr_forward(const b200gsr_params* prm, const float* means3D, const float
     return B200GSR_OK;
 }
 
-int b200gsr_backward(const b200gsr_params* prm, const float* means3D, const float* shs,
+int b200gsr_backward_ex(const b200gsr_params* prm, const float* means3D, const float* shs,
                      const float* colors_precomp, const float* opacities, const float* scales,
                      const float* rotations, const float* cov3D_precomp, const int32_t* radii,
                      const float* out_depth_alpha, const float* dL_dcolor,
                      const float* dL_ddepth_alpha, void* saved, size_t saved_bytes,
                      void* /*scratch*/, size_t /*scratch_bytes*/, uint64_t max_pairs, float* d_means3D,
                      float* d_means2D, float* d_shs, float* d_colors, float* d_opacities,
-                     float* d_scales, float* d_rotations, float* d_cov3D, void* stream) {
+                     float* d_scales, float* d_rotations, float* d_cov3D, uint32_t stages,
+                     int32_t g_begin, int32_t g_end, int32_t dsh_coefs, void* stream) {
     int rc = validate_inputs(prm, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp);
     if (rc) return rc;
     if (prm->P == 0) return B200GSR_OK;
+    if (g_begin < 0 || g_end > prm->P || g_begin > g_end || (g_begin % 128) != 0)
+        return fail(B200GSR_ERR_BAD_ARG, "bad Gaussian range [%d, %d): need 0 <= begin <= end <= P, begin %% 128 == 0", g_begin, g_end);
+    if (shs && dsh_coefs != 0 && (dsh_coefs < (prm->sh_degree + 1) * (prm->sh_degree + 1) || dsh_coefs > prm->M))
+        return fail(B200GSR_ERR_BAD_ARG, "dsh_coefs=%d must be 0 or in [(sh_degree+1)^2, M]", dsh_coefs);
     if (!radii || !out_depth_alpha || !dL_dcolor || !dL_ddepth_alpha || !saved)
         return fail(B200GSR_ERR_BAD_ARG, "null saved-state/gradient pointer");
     if (!d_means3D || !d_means2D || !d_opacities || (shs && !d_shs) || (colors_precomp && !d_colors) ||
@@ -269,24 +275,46 @@ int b200gsr_backward(const b200gsr_params* prm, const float* means3D, const floa
     a.max_pairs = (uint32_t)max_pairs;
     a.d_means3D = d_means3D; a.d_means2D = d_means2D; a.d_shs = d_shs; a.d_colors = d_colors;
     a.d_opac = d_opacities; a.d_scales = d_scales; a.d_rots = d_rotations; a.d_cov3d = d_cov3D;
-    a.num_sms = ds->num_sms;
+    a.num_sms = ds->num_sms; a.stats = g_stats;
+    a.g_begin = g_begin; a.g_end = g_end; a.dsh_coefs = dsh_coefs;
     a.stream = static_cast<cudaStream_t>(stream);
 
     // no memsets: the work-queue counters and the gradient accumulators live in `saved`, zeroed by
     // the forward and restored to zero by project_bwd
-    prof_mark_bwd(0, a.stream);
-    GSR_RANGE_PUSH("b200gsr.composite_bwd");
-    rc = check_cuda(gsr_launch_composite_bwd(a), "composite_bwd");
-    GSR_RANGE_POP();
-    if (rc) return rc;
-    prof_mark_bwd(1, a.stream);
-    GSR_RANGE_PUSH("b200gsr.project_bwd");
-    rc = check_cuda(gsr_launch_project_bwd(a), "project_bwd");
-    GSR_RANGE_POP();
-    if (rc) return rc;
-    prof_mark_bwd(2, a.stream);
-    if (g_prof.max_calls > 0 && g_prof.nbwd < g_prof.max_calls) ++g_prof.nbwd;
+    const bool whole = (stages & B200GSR_BWD_COMPOSITE) && (stages & B200GSR_BWD_PROJECT) && g_begin == 0 && g_end == prm->P;
+    if (stages & B200GSR_BWD_COMPOSITE) {
+        if (whole) prof_mark_bwd(0, a.stream);
+        GSR_RANGE_PUSH("b200gsr.composite_bwd");
+        rc = check_cuda(gsr_launch_composite_bwd(a), "composite_bwd");
+        GSR_RANGE_POP();
+        if (rc) return rc;
+    }
+    if (stages & B200GSR_BWD_PROJECT) {
+        if (whole) prof_mark_bwd(1, a.stream);
+        GSR_RANGE_PUSH("b200gsr.project_bwd");
+        rc = check_cuda(gsr_launch_project_bwd(a), "project_bwd");
+        GSR_RANGE_POP();
+        if (rc) return rc;
+    }
+    if (whole) {
+        prof_mark_bwd(2, a.stream);
+        if (g_prof.max_calls > 0 && g_prof.nbwd < g_prof.max_calls) ++g_prof.nbwd;
+    }
     return B200GSR_OK;
+}
+
+int b200gsr_backward(const b200gsr_params* prm, const float* means3D, const float* shs,
+                     const float* colors_precomp, const float* opacities, const float* scales,
+                     const float* rotations, const float* cov3D_precomp, const int32_t* radii,
+                     const float* out_depth_alpha, const float* dL_dcolor,
+                     const float* dL_ddepth_alpha, void* saved, size_t saved_bytes,
+                     void* scratch, size_t scratch_bytes, uint64_t max_pairs, float* d_means3D,
+                     float* d_means2D, float* d_shs, float* d_colors, float* d_opacities,
+                     float* d_scales, float* d_rotations, float* d_cov3D, void* stream) {
+    return b200gsr_backward_ex(prm, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, radii,
+                               out_depth_alpha, dL_dcolor, dL_ddepth_alpha, saved, saved_bytes, scratch, scratch_bytes,
+                               max_pairs, d_means3D, d_means2D, d_shs, d_colors, d_opacities, d_scales, d_rotations,
+                               d_cov3D, B200GSR_BWD_COMPOSITE | B200GSR_BWD_PROJECT, 0, prm ? prm->P : 0, 0, stream);
 }
 
 int b200gsr_profile_enable(int32_t max_calls) {
@@ -322,6 +350,11 @@ int b200gsr_profile_read(int32_t is_backward, int32_t call, float* ms) {
     for (int k = 0; k + 1 < ne; ++k)
         if ((e = cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1])) != cudaSuccess)
             return check_cuda(e, "cudaEventElapsedTime");
+    return B200GSR_OK;
+}
+
+int b200gsr_debug_counters(unsigned long long* device_counters) {
+    g_stats = device_counters;
     return B200GSR_OK;
 }
 

@@ -141,6 +141,7 @@ struct GsrFwdArgs {
     uint32_t notify_seq;
     uint32_t flags;        // B200GSR_FWD_*
     int num_sms;           // of the current device (cached per device in api.cu)
+    unsigned long long* stats;
     cudaStream_t stream;
 };
 
@@ -155,7 +156,10 @@ struct GsrBwdArgs {
     b200gsr_saved_layout vl;
     uint32_t max_pairs;
     float *d_means3D, *d_means2D, *d_shs, *d_colors, *d_opac, *d_scales, *d_rots, *d_cov3d;
+    int g_begin, g_end;    // Gaussian range of the project_bwd stage (chunked launches)
+    int dsh_coefs;         // coefficients per row of d_shs (0 = M, the reference layout)
     int num_sms;
+    unsigned long long* stats;   // optional device counters (b200gsr_debug_counters); selects the STATS kernels
     cudaStream_t stream;
 };
 

@@ -28,6 +28,12 @@ namespace {
 // ordered longest list first).  Every warp is an independent worker with a private ring of kSlots
 // sub-chunks (32 records = one per lane): the backward kernel contains no CTA-wide barrier.
 constexpr int kWarps = 8;      // warps per CTA (in the backward kernel just a container)
+#ifndef GSR_BWD_DEFAULT_VARIANT
+#define GSR_BWD_DEFAULT_VARIANT 10    // which backward kernel ships (see gsr_launch_composite_bwd)
+#endif
+#ifndef GSR_BWD_KFAST
+#define GSR_BWD_KFAST 2               // fast-path width of the STATS instantiation
+#endif
 // kSlots (template parameter of the backward kernel) = sub-chunks in the ring per warp
 // (kSlots-1 being gathered + 1 being blended); 1.5 KB per slot and warp.
 template <int kSlots>
@@ -94,6 +100,10 @@ __device__ __forceinline__ bool cull_pass(float px, float py, uint32_t ext, floa
     return (ddx <= e.x) && (ddy <= e.y);
 }
 
+// slots of the optional diagnostic counters (b200gsr_debug_counters)
+enum { GSR_STAT_BWD_EVAL = 0, GSR_STAT_BWD_CONTRIB = 1, GSR_STAT_BWD_LANES = 2, GSR_STAT_BWD_HIST = 3,   // 3..8
+       GSR_STAT_FWD_EVAL = 10, GSR_STAT_FWD_LANES = 11, GSR_STAT_WORDS = 16 };
+
 // =============================================================================================
 // Forward
 // =============================================================================================
@@ -109,7 +119,7 @@ struct __align__(128) SmemCta {
     uint32_t work;           // broadcast slot for the tile queue
 };
 
-template <bool SCORE, int PPL>
+template <bool SCORE, int PPL, bool STATS>
 __global__ void __launch_bounds__(256 / PPL)
 composite_fwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restrict__ header,
                      const uint32_t* __restrict__ work_order,
@@ -117,8 +127,10 @@ composite_fwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restric
                      const unsigned long long* __restrict__ keys, const GsrRec* __restrict__ geom,
                      const float* __restrict__ bg, uint32_t* __restrict__ queue,
                      float* __restrict__ out_color, float* __restrict__ out_depth_alpha,
-                     uint32_t* __restrict__ n_contrib, float* __restrict__ score) {
+                     uint32_t* __restrict__ n_contrib, float* __restrict__ score,
+                     unsigned long long* __restrict__ stats) {
     constexpr int kThreads = 256 / PPL;
+    unsigned int st_eval = 0, st_lanes = 0;
     constexpr int kPer = kChunk / kThreads;   // list entries gathered per thread per chunk
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SmemCta& sm = *reinterpret_cast<SmemCta*>(smem_raw);
@@ -203,6 +215,7 @@ composite_fwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restric
                     const float4* rp = sp + 3 * b;
                     const float4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
                     float wsum = 0.f;
+                    if (STATS) ++st_eval;
 #pragma unroll
                     for (int q = 0; q < PPL; ++q) {
                         const PairEval e = eval_pair(q0.x, q0.y, q0.w, q1.x, q1.y, q1.z, X, Y[q]);
@@ -219,6 +232,7 @@ composite_fwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restric
                                 T[q] = Tn;
                                 last[q] = pos0 + (uint32_t)b;
                                 if (SCORE) wsum += wgt;
+                                if (STATS) ++st_lanes;
                             }
                         }
                     }
@@ -248,6 +262,13 @@ composite_fwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restric
                 out_depth_alpha[plane + pix] = T[q];
                 n_contrib[pix] = last[q];
             }
+        }
+    }
+    if (STATS && stats != nullptr) {
+        const unsigned int tl = __reduce_add_sync(0xffffffffu, st_lanes);
+        if (lane == 0) {
+            atomicAdd(stats + GSR_STAT_FWD_EVAL, (unsigned long long)st_eval);
+            atomicAdd(stats + GSR_STAT_FWD_LANES, (unsigned long long)tl);
         }
     }
 }
@@ -419,6 +440,234 @@ composite_bwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restric
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Backward, round-2 variant ("v2"): same work decomposition and ring as composite_bwd_kernel, with an
+// instruction diet on the per-(warp, Gaussian) body:
+//   * branch-free: non-contributing lanes run the same arithmetic with alpha = G = 0 instead of a
+//     divergent block + ten zero-initialisations (BSSY/BSYNC, 8 moves gone);
+//   * packed fp32 (fma.rn.f32x2 / mul / add -> FFMA2, FMUL2, FADD2): the four channel-parallel
+//     streams (r, g, b, depth) and the (x, y) geometry pairs go two per instruction, halving the
+//     fma-pipe occupancy of the body (the fma pipe retires a 3-register FFMA every 2 cycles/SMSP);
+//   * small-footprint fast path: when at most KFAST lanes of the warp contribute, those lanes commit
+//     their ten partials directly with three vector reductions (red.global.add.v4.f32, sm_90+:
+//     dgeom rows are 3 x 16 B) instead of the 12-shuffle butterfly;
+//   * STATS instantiation counts evaluated / contributing (warp, Gaussian) pairs and the popcount
+//     histogram for the secondary (pair-evaluation) roofline in bench.py; never timed.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" :: "l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+// packed halving step on float2 pairs is not possible (selects are per register), but the ADDs are
+template <int N, int XOR>
+__device__ __forceinline__ void halve2(float (&v)[10], bool hi) {
+    constexpr int Hh = (N + 1) / 2;
+    float keep[Hh], recv[Hh];
+#pragma unroll
+    for (int k = 0; k < Hh; ++k) {
+        const float lo = v[k];
+        const float hv = (Hh + k < N) ? v[Hh + k] : 0.0f;
+        const float send = hi ? lo : hv;
+        keep[k] = hi ? hv : lo;
+        recv[k] = __shfl_xor_sync(0xffffffffu, send, XOR);
+    }
+#pragma unroll
+    for (int k = 0; k + 1 < Hh; k += 2) {
+        const float2 r = __fadd2_rn(make_float2(keep[k], keep[k + 1]), make_float2(recv[k], recv[k + 1]));
+        v[k] = r.x; v[k + 1] = r.y;
+    }
+    if (Hh & 1) v[Hh - 1] = keep[Hh - 1] + recv[Hh - 1];
+}
+
+
+template <int kSlots, int kMinCtas, int KFAST, bool STATS>
+__global__ void __launch_bounds__(kWarps * 32, kMinCtas)
+composite_bwd2_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restrict__ header,
+                      const uint32_t* __restrict__ work_order,
+                      const uint32_t* __restrict__ tile_start,
+                      const unsigned long long* __restrict__ keys, const GsrRec* __restrict__ geom,
+                      const float* __restrict__ bg, uint32_t* __restrict__ queue,
+                      const float* __restrict__ out_depth_alpha,
+                      const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dcolor,
+                      const float* __restrict__ dL_ddepth_alpha, float* __restrict__ dgeom,
+                      unsigned long long* __restrict__ stats) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SmemRing<kSlots>& sm = *reinterpret_cast<SmemRing<kSlots>*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    GsrRec (*ring)[32] = sm.rec[wid];
+    const uint32_t max_pairs = header[GSR_H_MAX_PAIRS];
+    const uint32_t nonempty = header[GSR_H_NUM_NONEMPTY];
+    const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
+    const int vidx = bwd_value_index(lane);
+    const bool commit_lane = (vidx >= 0) && !(lane & 1);
+    const size_t plane = (size_t)H * W;
+    unsigned long long st_eval = 0, st_contrib = 0, st_lanes = 0;
+    unsigned long long st_hist[6] = {0, 0, 0, 0, 0, 0};
+
+    uint32_t qsel = (blockIdx.x * kWarps + wid) % GSR_NQUEUE, qtried = 0;
+    for (;;) {
+        const uint32_t item = warp_pop(queue, nonempty * 8u, qsel, qtried, lane);   // empty tiles: no gradient
+        if (item == 0xffffffffu) break;
+        const uint32_t tile = work_order[item >> 3];
+        const int blk = (int)(item & 7u);
+        uint32_t beg = tile_start[tile], end = tile_start[tile + 1];
+        if (end > max_pairs) end = max_pairs;
+        if (beg > end) beg = end;
+        const unsigned long long* tk = keys + beg;
+        const int tyi = tile / gx, txi = tile - tyi * gx;
+        const int X0i = txi * GSR_TILE + (blk & 1) * 8, Y0i = tyi * GSR_TILE + (blk >> 1) * 4;
+        const int Xi = X0i + (lane & 7), Yi = Y0i + (lane >> 3);
+        const float X0 = (float)X0i, Y0 = (float)Y0i;
+        const float2 XY = make_float2(-(float)Xi, -(float)Yi);
+        uint32_t last = 0;
+        float Tfinal = 1.f, dT = 0.f;
+        float2 dC01 = make_float2(0.f, 0.f), dC2D = make_float2(0.f, 0.f);
+        if (Xi < W && Yi < H) {
+            const size_t pix = (size_t)Yi * W + Xi;
+            last = n_contrib[pix];
+            Tfinal = out_depth_alpha[plane + pix];
+            dC01.x = dL_dcolor[pix]; dC01.y = dL_dcolor[plane + pix]; dC2D.x = dL_dcolor[2 * plane + pix];
+            dC2D.y = dL_ddepth_alpha[pix]; dT = dL_ddepth_alpha[plane + pix];
+        }
+        if ((int)last > (int)(end - beg)) last = end - beg;   // overflow safety
+        const int n = (int)__reduce_max_sync(0xffffffffu, last);   // only entries [0, n) reached this block
+        const int nsub = (n + 31) >> 5;
+        const float bgT = Tfinal * (bg0 * dC01.x + bg1 * dC01.y + bg2 * dC2D.x + dT);   // Tfinal * bgterm
+        float T = Tfinal;
+        float2 acc01 = make_float2(0.f, 0.f), acc2D = make_float2(0.f, 0.f);
+
+        // sub-chunks are visited from the back: visit v <-> sub-chunk nsub-1-v
+        unsigned long long kq0, kq1;
+        {
+            unsigned long long kk[kSlots + 1];
+#pragma unroll
+            for (int j = 0; j < kSlots + 1; ++j) {
+                const int e = (nsub - 1 - j) * 32 + lane;
+                kk[j] = (j < nsub && e < n) ? __ldg(tk + e) : 0ull;
+            }
+#pragma unroll
+            for (int j = 0; j < kSlots - 1; ++j) {
+                const int e = (nsub - 1 - j) * 32 + lane;
+                if (j < nsub && e < n) gather_record(&ring[j][lane], geom, kk[j]);
+                cp_async_commit();
+            }
+            kq0 = kk[kSlots - 1]; kq1 = kk[kSlots];
+        }
+        for (int v = 0; v < nsub; ++v) {
+            {
+                const int g = v + kSlots - 1;
+                if (g < nsub) gather_record(&ring[g % kSlots][lane], geom, kq0);   // earlier sub-chunks are full
+                cp_async_commit();
+                kq0 = kq1;
+                const int g2 = v + kSlots + 1;
+                kq1 = (g2 < nsub) ? __ldg(tk + (nsub - 1 - g2) * 32 + lane) : 0ull;
+            }
+            cp_async_wait<kSlots - 1>();
+            __syncwarp();
+            const GsrRec* st = ring[v % kSlots];
+            const int sidx = nsub - 1 - v;
+            const int cnt = min(32, n - sidx * 32);
+            bool pass = false;
+            if (lane < cnt) {
+                const float4 q0 = *reinterpret_cast<const float4*>(&st[lane]);
+                pass = cull_pass(q0.x, q0.y, __float_as_uint(q0.z), X0, Y0);
+            }
+            uint32_t mask = __ballot_sync(0xffffffffu, pass);
+            const float4* sp = reinterpret_cast<const float4*>(st);
+            const uint32_t pos0 = (uint32_t)(sidx * 32 + 1);
+            while (mask) {
+                const int b = 31 - __clz(mask);
+                mask &= ~(1u << b);
+                const float4* rp = sp + 3 * b;
+                const float4 q0 = rp[0], q1 = rp[1];
+                const uint32_t pos = pos0 + (uint32_t)b;
+                // ---- the blending test (identical decisions to eval_pair) ----
+                const float2 d = __fadd2_rn(make_float2(q0.x, q0.y), XY);          // (dx, dy)
+#ifdef GSR_EXACT_EXP
+                const PairEval e = eval_pair(q0.x, q0.y, q0.w, q1.x, q1.y, q1.z, -XY.x, -XY.y);
+                const float G = e.G, alpha = e.alpha;
+                const bool valid = e.valid;
+#else
+                const float u = __fmaf_rn(q0.w, d.x, __fmul_rn(q1.x, d.y));
+                const float p2 = __fmaf_rn(__fmul_rn(q1.y, d.y), d.y, __fmul_rn(u, d.x));
+                const float G = ex2_approx(p2);
+                const float alpha = fminf(GSR_ALPHA_MAX, __fmul_rn(q1.z, G));
+                const bool valid = (p2 <= 0.0f) && (alpha >= GSR_ALPHA_MIN);
+#endif
+                const bool contrib = valid && pos <= last;
+                const uint32_t cm = __ballot_sync(0xffffffffu, contrib);
+                if (STATS) ++st_eval;
+                if (cm == 0u) continue;
+                const float4 q2 = rp[2];
+                // ---- branch-free body: non-contributing lanes carry alpha = G = 0 ----
+                const float am = contrib ? alpha : 0.0f;
+                const float Gm = contrib ? G : 0.0f;
+                const float rom = rcp_approx(1.0f - am);
+                T = contrib ? T * rom : T;                       // transmittance in front of this entry
+                const float wgt = am * T;
+                const float2 c01 = make_float2(q2.x, q2.y), c2D = make_float2(q2.z, q1.w);
+                const float2 nacc01 = make_float2(-acc01.x, -acc01.y), nacc2D = make_float2(-acc2D.x, -acc2D.y);
+                const float2 d01 = __fadd2_rn(c01, nacc01), d2D = __fadd2_rn(c2D, nacc2D);
+                const float2 dot2 = __ffma2_rn(d2D, dC2D, __fmul2_rn(d01, dC01));
+                const float dLda = (dot2.x + dot2.y) * T - bgT * rom;
+                const float2 am2 = make_float2(am, am);
+                acc01 = __ffma2_rn(am2, d01, acc01);
+                acc2D = __ffma2_rn(am2, d2D, acc2D);
+                float vv[10];
+                vv[5] = Gm * dLda;
+                const float gG = q1.z * vv[5];                   // dL/dG * G (no zeroing under the 0.99 clamp)
+#ifdef GSR_EXACT_EXP
+                const float2 gs = make_float2(-(q0.w * d.x + q1.x * d.y), -(q1.y * d.y + q1.x * d.x));
+#else
+                const float2 gs = __ffma2_rn(make_float2(q0.w + q0.w, q1.y + q1.y), d, __fmul2_rn(make_float2(q1.x, q1.x), make_float2(d.y, d.x)));
+#endif
+                const float2 gG2 = make_float2(gG, gG);
+                const float2 v01 = __fmul2_rn(gG2, gs);
+                const float2 tu = __fmul2_rn(gG2, d);             // (gG dx, gG dy)
+                const float2 v24 = __fmul2_rn(tu, d);             // (gG dx^2, gG dy^2)
+                vv[0] = v01.x; vv[1] = v01.y; vv[2] = v24.x; vv[3] = tu.x * d.y; vv[4] = v24.y;
+                const float2 w2 = make_float2(wgt, wgt);
+                const float2 v67 = __fmul2_rn(w2, dC01), v89 = __fmul2_rn(w2, dC2D);
+                vv[6] = v67.x; vv[7] = v67.y; vv[8] = v89.x; vv[9] = v89.y;
+                float* row = dgeom + 12 * (size_t)__float_as_uint(q2.w);
+                const int k = __popc(cm);
+                if (STATS) {
+                    ++st_contrib; st_lanes += k;
+                    ++st_hist[k == 1 ? 0 : k == 2 ? 1 : k <= 4 ? 2 : k <= 8 ? 3 : k <= 16 ? 4 : 5];
+                }
+                if (KFAST > 0 && k <= KFAST) {
+                    if (contrib) {
+                        red_add_v4(row, vv[0], vv[1], vv[2], vv[3]);
+                        red_add_v4(row + 4, vv[4], vv[5], vv[6], vv[7]);
+                        red_add_v2(row + 8, vv[8], vv[9]);
+                    }
+                    continue;
+                }
+                halve2<10, 16>(vv, lane & 16);
+                halve2<5, 8>(vv, lane & 8);
+                halve2<3, 4>(vv, lane & 4);
+                halve2<2, 2>(vv, lane & 2);
+                const float tot = vv[0] + __shfl_xor_sync(0xffffffffu, vv[0], 1);
+                if (commit_lane) atomicAdd(row + vidx, tot);
+            }
+            __syncwarp();
+        }
+        cp_async_wait<0>();
+        __syncwarp();
+    }
+    if (STATS && lane == 0 && stats != nullptr) {
+        atomicAdd(stats + GSR_STAT_BWD_EVAL, st_eval);
+        atomicAdd(stats + GSR_STAT_BWD_CONTRIB, st_contrib);
+        atomicAdd(stats + GSR_STAT_BWD_LANES, st_lanes);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) atomicAdd(stats + GSR_STAT_BWD_HIST + j, st_hist[j]);
+    }
+}
+
 }  // namespace
 
 struct CompPtrs {
@@ -440,15 +689,15 @@ static CompPtrs comp_ptrs(const uint8_t* saved, const b200gsr_saved_layout& vl, 
     return c;
 }
 
-template <bool SCORE>
+template <bool SCORE, bool STATS>
 static cudaError_t launch_fwd(const GsrFwdArgs& a, int nblocks, const CompPtrs& c, uint32_t* queue) {
     const int smem = (int)sizeof(SmemCta);
     static std::atomic<unsigned long long> attr_done{0};
-    cudaError_t e = gsr_smem_once(composite_fwd_kernel<SCORE, 1>, smem, attr_done);
+    cudaError_t e = gsr_smem_once(composite_fwd_kernel<SCORE, 1, STATS>, smem, attr_done);
     if (e != cudaSuccess) return e;
-    composite_fwd_kernel<SCORE, 1><<<nblocks, 256, smem, a.stream>>>(
+    composite_fwd_kernel<SCORE, 1, STATS><<<nblocks, 256, smem, a.stream>>>(
         a.prm.image_height, a.prm.image_width, c.grid.gx, c.grid.ntiles, c.header, c.work_order, c.tile_start,
-        c.keys, c.geom, a.prm.bg, queue, a.out_color, a.out_depth_alpha, c.n_contrib, a.score);
+        c.keys, c.geom, a.prm.bg, queue, a.out_color, a.out_depth_alpha, c.n_contrib, a.score, a.stats);
     return cudaGetLastError();
 }
 
@@ -457,7 +706,9 @@ cudaError_t gsr_launch_composite_fwd(const GsrFwdArgs& a) {
     if (c.grid.ntiles == 0) return cudaSuccess;
     uint32_t* queue = reinterpret_cast<uint32_t*>(a.scratch + a.sl.counters) + GSR_C_FWD_QUEUE;
     const int nblocks = min(c.grid.ntiles, a.num_sms * 6);
-    return a.prm.score_flag ? launch_fwd<true>(a, nblocks, c, queue) : launch_fwd<false>(a, nblocks, c, queue);
+    if (a.stats != nullptr)
+        return a.prm.score_flag ? launch_fwd<true, true>(a, nblocks, c, queue) : launch_fwd<false, true>(a, nblocks, c, queue);
+    return a.prm.score_flag ? launch_fwd<true, false>(a, nblocks, c, queue) : launch_fwd<false, false>(a, nblocks, c, queue);
 }
 
 template <int kSlots, int kMinCtas>
@@ -473,13 +724,38 @@ static cudaError_t launch_bwd(const GsrBwdArgs& a, const CompPtrs& c, uint32_t* 
     return cudaGetLastError();
 }
 
+template <int kSlots, int kMinCtas, int KFAST, bool STATS>
+static cudaError_t launch_bwd2(const GsrBwdArgs& a, const CompPtrs& c, uint32_t* queue, float* dgeom) {
+    const int smem = (int)sizeof(SmemRing<kSlots>);
+    const int nblocks = min(c.grid.ntiles, a.num_sms * kMinCtas);
+    static std::atomic<unsigned long long> attr_done{0};
+    cudaError_t e = gsr_smem_once(composite_bwd2_kernel<kSlots, kMinCtas, KFAST, STATS>, smem, attr_done);
+    if (e != cudaSuccess) return e;
+    composite_bwd2_kernel<kSlots, kMinCtas, KFAST, STATS><<<nblocks, kWarps * 32, smem, a.stream>>>(
+        a.prm.image_height, a.prm.image_width, c.grid.gx, c.grid.ntiles, c.header, c.work_order, c.tile_start,
+        c.keys, c.geom, a.prm.bg, queue, a.out_depth_alpha, c.n_contrib, a.dL_dcolor, a.dL_ddepth_alpha, dgeom,
+        a.stats);
+    return cudaGetLastError();
+}
+
 cudaError_t gsr_launch_composite_bwd(const GsrBwdArgs& a) {
     const CompPtrs c = comp_ptrs(a.saved, a.vl, a.prm.image_height, a.prm.image_width);
     if (c.grid.ntiles == 0) return cudaSuccess;
     uint32_t* queue = reinterpret_cast<uint32_t*>(a.saved + a.vl.header) + GSR_H_BWD_QUEUE;
     float* dgeom = reinterpret_cast<float*>(a.saved + a.vl.dgeom);
-    // ring depth x CTAs/SM: tuned default 3 x 4 (measured 0.253 ms; 4:0.260, 6:0.273, 8:0.282);
-    // B200GSR_BWD_SLOTS=2|25|35|4 selects other variants for A/B runs
+    if (a.stats != nullptr) return launch_bwd2<3, 4, GSR_BWD_KFAST, true>(a, c, queue, dgeom);
+    // B200GSR_BWD_VARIANT selects kernels for A/B runs (profiles/r02_bwd_ab.md): 0 = round-1 kernel,
+    // 10/11/12/14 = v2 with the direct-commit fast path for <= 0/1/2/4 contributing lanes;
+    // B200GSR_BWD_SLOTS = ring depth x CTAs/SM of the round-1 kernel (tuned default 3 x 4)
+    static const int variant = [] { const char* e = getenv("B200GSR_BWD_VARIANT"); return e ? atoi(e) : GSR_BWD_DEFAULT_VARIANT; }();
+    switch (variant) {
+        case 10: return launch_bwd2<3, 4, 0, false>(a, c, queue, dgeom);
+        case 11: return launch_bwd2<3, 4, 1, false>(a, c, queue, dgeom);
+        case 12: return launch_bwd2<3, 4, 2, false>(a, c, queue, dgeom);
+        case 14: return launch_bwd2<3, 4, 4, false>(a, c, queue, dgeom);
+        case 125: return launch_bwd2<3, 5, 2, false>(a, c, queue, dgeom);
+        default: break;
+    }
     static const int slots = [] { const char* e = getenv("B200GSR_BWD_SLOTS"); return e ? atoi(e) : 3; }();
     switch (slots) {
         case 2: return launch_bwd<2, 4>(a, c, queue, dgeom);

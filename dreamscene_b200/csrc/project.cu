@@ -399,24 +399,27 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
                    const float* __restrict__ scales, const float* __restrict__ rots,
                    const float* __restrict__ cov3d, const int32_t* __restrict__ radii,
                    float* __restrict__ dgeom, uint32_t* __restrict__ bwd_queue,
+                   int g_base, int g_end, int dsh_coefs,
                    float* __restrict__ d_means3D, float* __restrict__ d_means2D,
                    float* __restrict__ d_shs, float* __restrict__ d_colors,
                    float* __restrict__ d_opac, float* __restrict__ d_scales,
                    float* __restrict__ d_rots, float* __restrict__ d_cov3d) {
     extern __shared__ __align__(16) float sh_buf[];
     __shared__ uint8_t vis_s[kBlock];
-    const int g0 = blockIdx.x * kBlock;
+    // this launch covers Gaussians [g_base, g_end) (the whole range, or one chunk when the host
+    // overlaps the gradient all-reduce of finished chunks with the remaining ones)
+    const int g0 = g_base + blockIdx.x * kBlock;
     const int i = g0 + threadIdx.x;
-    const bool active = i < p.P;
+    const bool active = i < g_end;
     const bool vis = active && (__ldg(radii + i) > 0);
-    const int nsh = 3 * p.M;
+    const int nsh = 3 * dsh_coefs;          // floats per row of d_shs: 3*M (reference layout) or compact
     const int stride = sh_row_stride(p.M);
     const int deg = p.sh_degree;
     const int ncoef = (deg + 1) * (deg + 1);
     if (shs != nullptr) {
         vis_s[threadIdx.x] = vis;
         __syncthreads();
-        stage_sh_rows<MT>(shs, p.M, 3 * ncoef, g0, p.P, vis_s, sh_buf, stride);
+        stage_sh_rows<MT>(shs, p.M, 3 * ncoef, g0, g_end, vis_s, sh_buf, stride);
         __syncthreads();
     }
     float dmean[3] = {0.f, 0.f, 0.f};
@@ -427,7 +430,7 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
     float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float dcol[3] = {0.f, 0.f, 0.f};
     // composite_bwd (the previous kernel on the stream) has drained its work queue: reset it
-    if (blockIdx.x == 0 && threadIdx.x < GSR_NQUEUE) bwd_queue[threadIdx.x] = 0u;
+    if (g_base == 0 && blockIdx.x == 0 && threadIdx.x < GSR_NQUEUE) bwd_queue[threadIdx.x] = 0u;
 
     if (vis) {
         Cam C;
@@ -628,14 +631,23 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
         // drain the rows with coalesced stores (zeros for culled rows / inactive degrees)
         __syncthreads();
         const int nf = 3 * ncoef, nchunk = (nf + 3) >> 2;
-        if (MT > 0 && ((3 * MT) & 3) == 0) {
+        if (dsh_coefs != p.M) {
+            // compact rows (only the active degree's coefficients, e.g. the NCCL payload at sh_degree 0):
+            // the block's rows are one contiguous span of floats, written with coalesced 4-byte stores
+            const int rows = min(kBlock, g_end - g0);
+            float* base = d_shs + (size_t)g0 * nsh;
+            for (int f = threadIdx.x; f < rows * nsh; f += kBlock) {
+                const int row = f / nsh, col = f - row * nsh;
+                base[f] = (vis_s[row] && col < nf) ? sh_buf[row * stride + col] : 0.0f;
+            }
+        } else if (MT > 0 && ((3 * MT) & 3) == 0) {
             constexpr int q4 = (3 * (MT > 0 ? MT : 4)) / 4;
             float* base = d_shs + (size_t)g0 * 3 * MT;
 #pragma unroll
             for (int it = 0; it < q4; ++it) {
                 const int u = it * kBlock + threadIdx.x;
                 const int row = u / q4, c4 = u - row * q4;
-                if (g0 + row < p.P) {
+                if (g0 + row < g_end) {
                     float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (c4 < nchunk && vis_s[row]) val = *reinterpret_cast<const float4*>(sh_buf + row * stride + 4 * c4);
                     stg_na_f4(base + 4 * u, val);
@@ -647,7 +659,7 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
             const bool vec = (nsh & 3) == 0;
             for (int it = 0; it < kBlock / 8; ++it) {
                 const int row = it * 8 + w * 2 + hsel;
-                if (g0 + row >= p.P) continue;
+                if (g0 + row >= g_end) continue;
                 float* dst = d_shs + (size_t)(g0 + row) * nsh;
                 const bool v = vis_s[row];
                 if (vec) {
@@ -703,21 +715,22 @@ cudaError_t gsr_launch_project(const GsrFwdArgs& a) {
 }
 
 template <int MT>
-static void launch_project_bwd(const GsrBwdArgs& a, int P, size_t smem) {
-    project_bwd_kernel<MT><<<(P + kBlock - 1) / kBlock, kBlock, smem, a.stream>>>(
+static void launch_project_bwd(const GsrBwdArgs& a, int g_begin, int g_end, size_t smem) {
+    project_bwd_kernel<MT><<<(g_end - g_begin + kBlock - 1) / kBlock, kBlock, smem, a.stream>>>(
         a.prm, a.means3D, a.shs, a.colors, a.scales, a.rots, a.cov3d, a.radii,
         reinterpret_cast<float*>(a.saved + a.vl.dgeom),
-        reinterpret_cast<uint32_t*>(a.saved + a.vl.header) + GSR_H_BWD_QUEUE, a.d_means3D, a.d_means2D, a.d_shs,
+        reinterpret_cast<uint32_t*>(a.saved + a.vl.header) + GSR_H_BWD_QUEUE, g_begin, g_end,
+        a.dsh_coefs > 0 ? a.dsh_coefs : a.prm.M, a.d_means3D, a.d_means2D, a.d_shs,
         a.d_colors, a.d_opac, a.d_scales, a.d_rots, a.d_cov3d);
 }
 
 cudaError_t gsr_launch_project_bwd(const GsrBwdArgs& a) {
-    const int P = a.prm.P;
-    if (P == 0) return cudaSuccess;
+    const int g_begin = a.g_begin, g_end = a.g_end;
+    if (g_end <= g_begin) return cudaSuccess;
     const size_t smem = a.shs ? (size_t)kBlock * sh_row_stride(a.prm.M) * sizeof(float) : 0;
-    if (a.shs && a.prm.M == 16) launch_project_bwd<16>(a, P, smem);
-    else if (a.shs && a.prm.M == 4) launch_project_bwd<4>(a, P, smem);
-    else launch_project_bwd<0>(a, P, smem);
+    if (a.shs && a.prm.M == 16) launch_project_bwd<16>(a, g_begin, g_end, smem);
+    else if (a.shs && a.prm.M == 4) launch_project_bwd<4>(a, g_begin, g_end, smem);
+    else launch_project_bwd<0>(a, g_begin, g_end, smem);
     return cudaGetLastError();
 }
 

@@ -2,29 +2,57 @@
 
 DreamScene renders the C_batch_size views of a step sequentially on one GPU and lets autograd
 sum the per-view parameter gradients (/root/reference/training/scene_trainer.py:801-829,881).
-Here each rank renders its own views with replicated Gaussian parameters; the rasterizer's
-backward all-reduces (SUM) its flat parameter-gradient buffer over NCCL/NVLink before returning,
-so every rank ends the step with the same summed gradients as the sequential loop.
-Per-view quantities (means2D grad, radii, visibility) are NOT reduced, as in the reference,
-which only uses the last view's (training/object_trainer.py:385-390).
+Here each rank renders its own views with replicated Gaussian parameters and the per-view gradients
+are summed over NCCL/NVLink.  Two ways to do the sum, both additive to the reference API:
+
+1. ``all_reduce_gradients(params)`` after ``loss.backward()``  (DDP-style, ALWAYS exact).
+   One coalesced NCCL all-reduce over the leaf ``.grad`` tensors.  Correct for any graph between the
+   parameters and the rasterizer - in particular for the per-call random scale/SH augmentation of
+   ``scene_render`` (/root/reference/scene_gaussian.py:848-856), where every rank back-propagates
+   through its OWN random Jacobian.  Columns that are identically zero on every rank (SH
+   coefficients above the active degree: ``sh_degree`` starts at 0 and rises every 500 steps,
+   /root/reference/training/object_trainer.py:243-244) can be left out of the payload.
+
+2. ``enable_view_sharding(mode="backward")``: the rasterizer's backward all-reduces its flat
+   parameter-gradient buffer itself, chunk by chunk, overlapping the reduction of finished chunks
+   with the per-Gaussian backward of the remaining ones, and sends only the active degree's SH
+   columns.  This reduces the gradient AT THE RASTERIZER INPUTS, so it equals the sequential sum
+   only when the map parameters -> rasterizer inputs is the same deterministic function on every
+   rank (inputs are leaves, or activations without per-rank randomness).  Every rank must issue the
+   same sequence of rasterizer backward calls with the same P; set B200GSR_CHECK_COLLECTIVES=1 to
+   verify that at run time.  ``no_sync()`` suspends the reduction while a rank accumulates several
+   local views and reduces once with the last one.
+
+Per-view quantities (means2D grad, radii, visibility) are NOT reduced, as in the reference, which only
+uses the last view's (training/object_trainer.py:385-390).
 """
 from __future__ import annotations
 
-from typing import Optional
+import contextlib
+import os
+from typing import Iterable, Optional, Sequence
 
 import torch
 import torch.distributed as dist
 
 _group = None
 _enabled = False
+_chunks = 8
+_suspended = 0
+_CHECK = bool(int(os.environ.get("B200GSR_CHECK_COLLECTIVES", "0")))
 
 
-def enable_view_sharding(group: Optional["dist.ProcessGroup"] = None) -> None:
-    """After this call every rasterizer backward all-reduces its parameter gradients."""
-    global _group, _enabled
+def enable_view_sharding(group: Optional["dist.ProcessGroup"] = None, mode: str = "backward", chunks: int = 8) -> None:
+    """mode="backward": every rasterizer backward all-reduces its parameter gradients (see the module
+    docstring for when that is exact); mode="deferred": nothing happens inside backward, call
+    all_reduce_gradients() yourself.  `chunks` = number of Gaussian ranges the in-backward
+    reduction is pipelined over."""
+    global _group, _enabled, _chunks
     if not dist.is_initialized():
         raise RuntimeError("torch.distributed is not initialised")
-    _group, _enabled = group, True
+    if mode not in ("backward", "deferred"):
+        raise ValueError("mode must be 'backward' or 'deferred'")
+    _group, _enabled, _chunks = group, mode == "backward", max(1, int(chunks))
 
 
 def disable_view_sharding() -> None:
@@ -36,15 +64,124 @@ def is_enabled() -> bool:
     return _enabled
 
 
+@contextlib.contextmanager
+def no_sync():
+    """Suspend the in-backward reduction (accumulate several local views, reduce with the last)."""
+    global _suspended
+    _suspended += 1
+    try:
+        yield
+    finally:
+        _suspended -= 1
+
+
+def reduction_active() -> bool:
+    return _enabled and _suspended == 0 and dist.is_initialized() and dist.get_world_size(_group) > 1
+
+
+def chunk_bounds(P: int, chunks: Optional[int] = None, align: int = 128):
+    """Split [0, P) into <= chunks ranges whose starts are multiples of `align`."""
+    chunks = _chunks if chunks is None else chunks
+    if P <= 0:
+        return []
+    per = -(-P // chunks)
+    per = max(align, -(-per // align) * align)
+    return [(g, min(P, g + per)) for g in range(0, P, per)]
+
+
+def _coalesced_all_reduce(tensors, group, async_ops: bool):
+    """One NCCL group call for all tensors (ncclGroupStart/End); plain per-tensor calls on backends
+    without coalescing support (gloo in the CPU tests).  Returns an object with .wait()."""
+    if dist.get_backend(group) == "nccl":
+        with dist._coalescing_manager(group=group, device=tensors[0].device, async_ops=async_ops) as cm:
+            for t in tensors:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return cm
+    works = [dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=async_ops) for t in tensors]
+
+    class _Works:
+        def wait(self):
+            for w in works:
+                if w is not None:
+                    w.wait()
+    return _Works()
+
+
+def _check_same_size(numel: int, device="cuda") -> None:
+    t = torch.tensor([numel, -numel], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=_group)
+    if int(t[0]) != numel or int(t[1]) != -numel:
+        raise RuntimeError(f"view sharding: ranks disagree on the gradient buffer size ({numel} here, "
+                           f"max {int(t[0])}, min {-int(t[1])}): every rank must render the same P")
+
+
+class ChunkReducer:
+    """Issues one coalesced, asynchronous all-reduce per finished chunk (NCCL runs it on its own
+    stream after the kernels enqueued so far; the next chunk's kernel overlaps it)."""
+
+    def __init__(self, flat_numel: int, device="cuda"):
+        if _CHECK:
+            _check_same_size(flat_numel, device)
+        self.works = []
+
+    def reduce(self, pieces: Sequence[torch.Tensor]) -> None:
+        pieces = [p for p in pieces if p.numel() > 0]
+        if pieces:
+            self.works.append(_coalesced_all_reduce(pieces, _group, async_ops=True))
+
+    def wait(self) -> None:
+        for w in self.works:
+            w.wait()
+        self.works = []
+
+
 def maybe_all_reduce(flat: torch.Tensor) -> None:
-    if _enabled and dist.get_world_size(_group) > 1:
+    """Monolithic reduction of a flat buffer (used when chunking does not apply)."""
+    if reduction_active():
+        if _CHECK:
+            _check_same_size(flat.numel(), flat.device)
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=_group)
 
 
-def shard_views(num_views: int, rank: Optional[int] = None, world: Optional[int] = None):
-    """Views {rank, rank+world, ...} of a batch (scene_trainer.py:801 loop index i)."""
+def all_reduce_gradients(params: Iterable[torch.Tensor], group: Optional["dist.ProcessGroup"] = None,
+                         active_columns: Optional[dict] = None) -> None:
+    """DDP-style: sum the leaf gradients over the ranks with ONE coalesced NCCL all-reduce.  Exact for
+    any graph between parameters and rasterizer.  `active_columns` = {param: k}: only
+    ``param.grad[:, :k]`` can be non-zero on any rank (e.g. features_rest [P, M-1, 3] with
+    k = (sh_degree+1)^2 - 1), the rest is not sent."""
+    if not dist.is_initialized() or dist.get_world_size(group) <= 1:
+        return
+    active_columns = active_columns or {}
+    jobs = []          # (destination view or None, tensor handed to NCCL)
+    for p in params:
+        g = p.grad
+        if g is None:
+            continue
+        k = active_columns.get(p)
+        if k is not None and g.dim() >= 2 and k < g.shape[1]:
+            if k > 0:
+                jobs.append((g[:, :k], g[:, :k].contiguous()))       # packed copy of the active columns
+        elif g.is_contiguous():
+            jobs.append((None, g))                                     # reduced in place
+        else:
+            jobs.append((g, g.contiguous()))
+    if not jobs:
+        return
+    _coalesced_all_reduce([t for _, t in jobs], group, async_ops=False)
+    for dst, t in jobs:
+        if dst is not None:
+            dst.copy_(t)
+
+
+def shard_views(num_views: int, rank: Optional[int] = None, world: Optional[int] = None, allow_uneven: bool = False):
+    """Views {rank, rank+world, ...} of a batch (scene_trainer.py:801 loop index i).  With the
+    in-backward reduction every rank must own the same number of views (a collective per backward):
+    uneven shards are refused unless allow_uneven (use mode="deferred" + all_reduce_gradients then)."""
     if rank is None:
         rank = dist.get_rank(_group) if dist.is_initialized() else 0
     if world is None:
         world = dist.get_world_size(_group) if dist.is_initialized() else 1
+    if num_views % world != 0 and not allow_uneven:
+        raise ValueError(f"{num_views} views do not divide over {world} ranks: ranks would issue different numbers "
+                         "of collectives; pad the batch or pass allow_uneven=True with mode='deferred'")
     return list(range(rank, num_views, world))

@@ -61,7 +61,8 @@ class PairCapacityOverflow(RuntimeError):
 class _Device:
     def __init__(self, device: torch.device):
         self.device = device
-        self.capacity = 0            # pair capacity used for the next call (only ever grows)
+        self.capacity = 0            # pair capacity used for the next call (only ever grows for a given shape)
+        self.cap_key = None          # (P, H, W) the capacity was measured for: a new shape is re-measured
         self.user_capacity = False   # set by set_workspace_capacity: trust it, never wait on it
         self.last_pairs = 0          # pair count of the most recent RESOLVED forward
         self.seq = 0
@@ -110,8 +111,9 @@ def set_pair_count_mode(mode: str) -> None:
     "async" : (default) no host wait at all.  The capacity is 2x the largest D seen on the device
               (at least 4 pairs per Gaussian); the count of every forward is read lazily - without
               blocking - at later API calls, and an overflow (practically impossible with that
-              head-room) raises PairCapacityOverflow then.  The first forward on a device, which
-              establishes the capacity, is always synchronous unless set_workspace_capacity was called.
+              head-room) raises PairCapacityOverflow then.  The first forward with a new (P, H, W)
+              - a new scene, a densification step - measures its capacity synchronously, unless
+              set_workspace_capacity was called.
     Also settable with the environment variable B200GSR_PAIR_MODE."""
     global _pair_mode
     if mode not in ("sync", "async"):
@@ -252,7 +254,9 @@ def _forward_impl(rs, means3D, shs, colors, opac, scales, rots, cov3d, with_back
         stream_h = torch.cuda.current_stream(dev).cuda_stream
         stream = C.c_void_p(stream_h)
         flags = 0 if with_backward else _lib.FWD_NO_BACKWARD
-        known = d.capacity > 0
+        known = d.capacity > 0 and (d.user_capacity or d.cap_key == (P, H, W))
+        if capturing and d.capacity > 0:
+            known = True                   # cannot wait inside a capture: trust the high-water mark
         if capturing and not known:
             raise RuntimeError("b200gsr: capturing into a CUDA graph needs a known pair capacity: run one eager "
                                "forward on this device first or call set_workspace_capacity()")
@@ -299,9 +303,12 @@ def _forward_impl(rs, means3D, shs, colors, opac, scales, rots, cov3d, with_back
             d.last_pairs = pairs
             if pairs <= cap:
                 # high-water mark with 2x head-room: capacity only costs 8 B per pair in `saved`, and
-                # views of one training step differ a lot in pair count (random cameras); never shrinks
+                # views of one training step differ a lot in pair count (random cameras).  A new
+                # shape starts its own high-water mark.
                 if not d.user_capacity:
-                    d.capacity = max(d.capacity, _round_cap(2 * pairs))
+                    fresh = d.cap_key != (P, H, W)
+                    d.capacity = _round_cap(2 * pairs) if fresh else max(d.capacity, _round_cap(2 * pairs))
+                    d.cap_key = (P, H, W)
                 break
             cap = d.capacity = _round_cap(2 * pairs)   # overflow: re-issue with enough room
             if score is not None:
@@ -368,24 +375,30 @@ class _RasterizeGaussians(torch.autograd.Function):
         g_color = torch.zeros(3, H, W, device=dev) if g_color is None else _f32c(g_color)
         g_da = torch.zeros(2, H, W, device=dev) if g_da is None else _f32c(g_da)
 
-        # one flat buffer for every parameter gradient: a single NCCL all-reduce when views are
-        # sharded across ranks (dreamscene_b200.parallel), and one allocation otherwise
-        n_col = 3 * M if has_sh else 3
+        # one flat buffer for every parameter gradient.  Under view sharding (dreamscene_b200.parallel,
+        # mode "backward") it is all-reduced chunk by chunk while later chunks are still being computed,
+        # and the SH section holds only the active degree's coefficients (the payload at sh_degree 0 is
+        # 14 instead of 59 floats per Gaussian); otherwise it is simply one allocation.
+        reduce = P > 0 and _parallel.reduction_active()
+        ncoef = (int(rs.sh_degree) + 1) ** 2
+        compact = reduce and has_sh and ncoef < M
+        n_col = (3 * ncoef if compact else 3 * M) if has_sh else 3
         offs, o = grad_sections(P, n_col, has_sr)
         flat = torch.empty(max(o, 1), dtype=torch.float32, device=dev)
-        sec = lambda name, wdt: flat[offs[name]:offs[name] + P * wdt]
-        d_means3D = sec("means3D", 3).view(P, 3)
-        d_opac = sec("opac", 1).view(P, 1)
-        d_colsh = sec("col", n_col)
-        d_sh = d_colsh.view(P, M, 3) if has_sh else None
+        widths = {"means3D": 3, "opac": 1, "col": n_col, "scales": 3, "rots": 4, "cov": 6}
+        sec = lambda name, g0=0, g1=P: flat[offs[name] + g0 * widths[name]:offs[name] + g1 * widths[name]]
+        d_means3D = sec("means3D").view(P, 3)
+        d_opac = sec("opac").view(P, 1)
+        d_colsh = sec("col")
+        d_sh = d_colsh.view(P, n_col // 3, 3) if has_sh else None
         d_colors = d_colsh.view(P, 3) if has_col else None
         if has_sr:
-            d_scales = sec("scales", 3).view(P, 3)
-            d_rots = sec("rots", 4).view(P, 4)
+            d_scales = sec("scales").view(P, 3)
+            d_rots = sec("rots").view(P, 4)
             d_cov = None
         else:
             d_scales = d_rots = None
-            d_cov = sec("cov", 6).view(P, 6)
+            d_cov = sec("cov").view(P, 6)
         d_means2D = torch.empty(P, 3, dtype=torch.float32, device=dev)
 
         if P > 0:
@@ -398,15 +411,31 @@ class _RasterizeGaussians(torch.autograd.Function):
             with torch.cuda.device(dev):
                 prm = _make_params(rs, P, M, keep, dev)
                 stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-                rc = lib.b200gsr_backward(
-                    C.byref(prm), _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(opacities), _ptr(scales),
-                    _ptr(rots), _ptr(cov3d), _ptr(radii), _ptr(depth_alpha), _ptr(g_color), _ptr(g_da),
-                    _ptr(st.saved), st.saved.numel(), None, 0, st.capacity,
-                    _ptr(d_means3D), _ptr(d_means2D), _ptr(d_sh), _ptr(d_colors), _ptr(d_opac),
-                    _ptr(d_scales), _ptr(d_rots), _ptr(d_cov), stream)
-            if rc:
-                raise RuntimeError(f"b200gsr_backward failed ({rc}): {_lib.last_error()}")
-            _parallel.maybe_all_reduce(flat)
+
+                def launch(stages, g0, g1):
+                    rc = lib.b200gsr_backward_ex(
+                        C.byref(prm), _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(opacities), _ptr(scales),
+                        _ptr(rots), _ptr(cov3d), _ptr(radii), _ptr(depth_alpha), _ptr(g_color), _ptr(g_da),
+                        _ptr(st.saved), st.saved.numel(), None, 0, st.capacity,
+                        _ptr(d_means3D), _ptr(d_means2D), _ptr(d_sh), _ptr(d_colors), _ptr(d_opac),
+                        _ptr(d_scales), _ptr(d_rots), _ptr(d_cov), stages, g0, g1, ncoef if compact else 0, stream)
+                    if rc:
+                        raise RuntimeError(f"b200gsr_backward failed ({rc}): {_lib.last_error()}")
+
+                if not reduce:
+                    launch(_lib.BWD_COMPOSITE | _lib.BWD_PROJECT, 0, P)
+                else:
+                    red = _parallel.ChunkReducer(flat.numel(), dev)
+                    launch(_lib.BWD_COMPOSITE, 0, 0)
+                    names = [k for k in ("means3D", "opac", "col", "scales", "rots", "cov") if k in offs]
+                    for g0, g1 in _parallel.chunk_bounds(P):
+                        launch(_lib.BWD_PROJECT, g0, g1)
+                        red.reduce([sec(k, g0, g1) for k in names])
+                    red.wait()
+            if compact:                      # expand to the reference layout [P, M, 3] (zeros above the degree)
+                full = torch.zeros(P, M, 3, dtype=torch.float32, device=dev)
+                full[:, :ncoef] = d_sh
+                d_sh = full
         return (d_means3D, d_means2D, d_sh, d_colors, d_opac, d_scales, d_rots, d_cov, None)
 
 

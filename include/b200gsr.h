@@ -152,6 +152,34 @@ int b200gsr_backward(const b200gsr_params* prm,
                      float* d_opacities, float* d_scales, float* d_rotations, float* d_cov3D,
                      void* stream);
 
+/*
+ * Staged / chunked backward (additive; no upstream equivalent).  Same arguments as
+ * b200gsr_backward plus
+ *   stages    : B200GSR_BWD_COMPOSITE (per-pixel replay -> screen-space accumulators in `saved`)
+ *               and/or B200GSR_BWD_PROJECT (accumulators -> parameter gradients);
+ *   [g_begin, g_end) : the Gaussians the PROJECT stage covers (g_begin a multiple of 128).  The
+ *               host issues COMPOSITE once, then PROJECT chunk by chunk, all-reducing finished chunks
+ *               on a communication stream while the next chunk computes (dreamscene_b200.parallel);
+ *               every Gaussian must be covered exactly once per backward (read-and-clear);
+ *   dsh_coefs : 0 = d_shs has the reference layout [P, M, 3]; otherwise d_shs is a COMPACT
+ *               [P, dsh_coefs, 3] array holding only the coefficients an active degree can touch
+ *               ((sh_degree+1)^2 <= dsh_coefs <= M): the multi-GPU gradient payload at low degrees.
+ */
+#define B200GSR_BWD_COMPOSITE 1u
+#define B200GSR_BWD_PROJECT 2u
+int b200gsr_backward_ex(const b200gsr_params* prm,
+                        const float* means3D, const float* shs, const float* colors_precomp,
+                        const float* opacities, const float* scales, const float* rotations,
+                        const float* cov3D_precomp,
+                        const int32_t* radii, const float* out_depth_alpha,
+                        const float* dL_dcolor, const float* dL_ddepth_alpha,
+                        void* saved, size_t saved_bytes, void* scratch, size_t scratch_bytes,
+                        uint64_t max_pairs,
+                        float* d_means3D, float* d_means2D, float* d_shs, float* d_colors,
+                        float* d_opacities, float* d_scales, float* d_rotations, float* d_cov3D,
+                        uint32_t stages, int32_t g_begin, int32_t g_end, int32_t dsh_coefs,
+                        void* stream);
+
 /* Frustum test only (replaces _C.mark_visible; DreamScene never calls it): visible[P] bytes. */
 int b200gsr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
                          const float* projmatrix, uint8_t* visible, void* stream);
@@ -175,6 +203,17 @@ int b200gsr_dist2_knn3(int32_t P, const float* points, float* out, void* scratch
  * enable(0) frees everything.
  */
 int b200gsr_profile_enable(int32_t max_calls);
+/*
+ * Diagnostics (no upstream equivalent; process-wide, not thread-safe): while `device_counters`
+ * (16 zero-initialised uint64 in device memory) is set, the composite kernels run in their
+ * instrumented instantiation and accumulate
+ *   [0] (warp, Gaussian) pairs evaluated by the backward  [1] ... with >= 1 contributing pixel
+ *   [2] contributing (pixel, Gaussian) pairs              [3..8] histogram of contributing lanes per
+ *   pair: 1, 2, 3-4, 5-8, 9-16, 17-32                     [10] pairs evaluated by the forward
+ *   [11] blended (pixel, Gaussian) pairs in the forward.
+ * bench.py uses them (outside the timed region) for the pair-evaluation roofline.  NULL switches back.
+ */
+int b200gsr_debug_counters(unsigned long long* device_counters);
 int b200gsr_profile_counts(int32_t* n_forward, int32_t* n_backward);
 int b200gsr_profile_read(int32_t is_backward, int32_t call, float* ms);
 

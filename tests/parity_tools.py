@@ -83,9 +83,19 @@ def oracle_lists(sc, cam, deg, scale_modifier=1.0):
     return S, pre, keys, pl, ranges, dec
 
 
-def oracle_backward_on_tiles(sc, cam, deg, tiles, gc, gd, dec, dtype=torch.float64, group=6):
+def record_blend_decisions(pre32, dec, S, tiles):
+    """fp32 blend pass over `tiles` that records the per-(entry, pixel) blend decisions (see
+    oracle.splat_ref.composite) for replay by the fp64 gradient evaluation."""
+    rec = {}
+    with torch.no_grad():
+        O.composite(pre32, dec["point_list"], dec["ranges"], S, tiles=tiles, record_blend=rec)
+    return rec
+
+
+def oracle_backward_on_tiles(sc, cam, deg, tiles, gc, gd, dec, dtype=torch.float64, group=6, blend=None):
     """Complete parameter gradients of  sum(color*gc) + sum(depth_alpha*gd)  where gc/gd are already
-    zero outside `tiles`; blending in `dtype` on the fp32 decisions `dec`."""
+    zero outside `tiles`; blending in `dtype` on the fp32 decisions `dec` (and, when `blend` holds the
+    recorded fp32 per-pixel blend decisions, on exactly those as well)."""
     S = U.oracle_settings(cam, deg)
     names = ("means3D", "opacities", "shs", "scales", "rotations")
     t = {k: sc[k].detach().clone().requires_grad_(True) for k in names}
@@ -102,7 +112,8 @@ def oracle_backward_on_tiles(sc, cam, deg, tiles, gc, gd, dec, dtype=torch.float
     gc, gd = gc.to(dtype), gd.to(dtype)
     tiles = list(tiles)
     for i in range(0, len(tiles), group):
-        color, da, _, _ = O.composite(pre2, dec["point_list"], dec["ranges"], S, dtype, tiles=tiles[i:i + group])
+        color, da, _, _ = O.composite(pre2, dec["point_list"], dec["ranges"], S, dtype, tiles=tiles[i:i + group],
+                                      replay_blend=blend)
         loss = (color * gc).sum() + (da * gd).sum()
         g = torch.autograd.grad(loss, leaves, allow_unused=True)
         for a, gi in zip(acc, g):

@@ -35,7 +35,7 @@ def test_cfg1_full_backward_10k_256_all_six_gradients():
     sc, cam, deg = U.make_inputs(10000, H, W)
     g = torch.Generator().manual_seed(7)
     grads = (torch.randn(3, H, W, generator=g) / (H * W), torch.randn(2, H, W, generator=g) / (H * W))
-    ref32 = run_oracle(sc, cam, deg)
+    ref32 = run_oracle(sc, cam, deg, record=True)      # + the fp32 per-pixel blend decisions
     ref = run_oracle(sc, cam, deg, grads=grads, dtype=torch.float64, decisions=ref32["decisions"])
     cu = run_cuda(sc, cam, deg, grads=grads)
     st = PT.forward_stats(cu["color"], cu["depth_alpha"], ref32["color"], ref32["depth_alpha"])
@@ -60,7 +60,8 @@ def test_cfg2_forward_lists_and_sampled_backward(name, P):
     tiles = PT.sample_tiles(ref["ranges"], 24)
     mask = PT.tile_mask(tiles, H, W)
     gc, gd = _masked_grads(H, W, mask, seed=11)
-    want = PT.oracle_backward_on_tiles(sc, cam, deg, tiles, gc, gd, ref["decisions"])
+    blend = PT.record_blend_decisions(ref["pre"], ref["decisions"], U.oracle_settings(cam, deg), tiles)
+    want = PT.oracle_backward_on_tiles(sc, cam, deg, tiles, gc, gd, ref["decisions"], blend=blend)
     got = PT.cuda_forward_backward(sc, cam, deg, gc, gd)
     errs = PT.grad_errors(got["grads"], want)
     for k in GRAD_KEYS:

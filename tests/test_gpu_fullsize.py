@@ -146,7 +146,8 @@ def test_sampled_tiles_match_the_oracle_at_full_size(big):
     g = torch.Generator().manual_seed(13)
     gc = torch.randn(3, H, W, generator=g) / (H * W) * mask
     gd = torch.randn(2, H, W, generator=g) / (H * W) * mask
-    want = PT.oracle_backward_on_tiles(sc, cam, deg, tiles, gc, gd, odec, group=3)
+    blend = PT.record_blend_decisions(pre, odec, S, tiles)        # fp32 per-pixel decisions, replayed in fp64
+    want = PT.oracle_backward_on_tiles(sc, cam, deg, tiles, gc, gd, odec, group=3, blend=blend)
     got = PT.cuda_forward_backward(sc, cam, deg, gc, gd, device=dev)
     errs = PT.grad_errors(got["grads"], want)
     for k in ("means3D", "scales", "rotations", "opacities", "shs", "means2D"):

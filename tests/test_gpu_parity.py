@@ -48,7 +48,9 @@ def run_cuda(sc, cam, deg, score=False, grads=None, bg=(1.0, 1.0, 1.0), use="sh+
 
 
 def run_oracle(sc, cam, deg, score=False, grads=None, bg=(1.0, 1.0, 1.0), use="sh+sr", dtype=torch.float32,
-               decisions=None, scale_modifier=1.0):
+               decisions=None, scale_modifier=1.0, record=False):
+    """record=True: an fp32 run also records its per-(entry, pixel) blend decisions; they travel in
+    r["decisions"] and an fp64 run given those decisions replays them (oracle.splat_ref.composite)."""
     S = U.oracle_settings(cam, deg, bg, score, scale_modifier)
     t = {k: v.detach().clone().requires_grad_(grads is not None) for k, v in sc.items()}
     m2d = torch.zeros(t["means3D"].shape[0], 3, requires_grad=grads is not None)
@@ -61,7 +63,7 @@ def run_oracle(sc, cam, deg, score=False, grads=None, bg=(1.0, 1.0, 1.0), use="s
         kw["cov3D_precomp"] = t["cov3D_precomp"]
     else:
         kw["scales"] = t["scales"]; kw["rotations"] = t["rotations"]
-    r = O.rasterize(S, dtype=dtype, decisions=decisions, **kw)
+    r = O.rasterize(S, dtype=dtype, decisions=decisions, record_blend={} if record else None, **kw)
     if grads is not None:
         gc, gd = grads
         loss = (r["color"] * gc.to(dtype)).sum() + (r["depth_alpha"] * gd.to(dtype)).sum()
@@ -121,7 +123,7 @@ def test_backward_matches_fp64_oracle_on_fp32_lists():
     H = W = 128
     g = torch.Generator().manual_seed(1)
     grads = (torch.randn(3, H, W, generator=g) / (H * W), torch.randn(2, H, W, generator=g) / (H * W))
-    ref32 = run_oracle(sc, cam, deg)
+    ref32 = run_oracle(sc, cam, deg, record=True)
     ref = run_oracle(sc, cam, deg, grads=grads, dtype=torch.float64, decisions=ref32["decisions"])
     cu = run_cuda(sc, cam, deg, grads=grads)
     check_images(cu, ref32)
@@ -137,7 +139,7 @@ def test_sh_degrees_and_strides(deg, sh_max):
     H = W = 96
     g = torch.Generator().manual_seed(2)
     grads = (torch.randn(3, H, W, generator=g), torch.randn(2, H, W, generator=g))
-    ref32 = run_oracle(sc, cam, deg)
+    ref32 = run_oracle(sc, cam, deg, record=True)
     ref = run_oracle(sc, cam, deg, grads=grads, dtype=torch.float64, decisions=ref32["decisions"])
     cu = run_cuda(sc, cam, deg, grads=grads)
     check_images(cu, ref32)
@@ -204,7 +206,7 @@ def test_zero_scales_and_no_grad_mode():
     sc["scales"][1::7, 1] = 0.0
     H = W = 96
     grads = (torch.ones(3, H, W) / 100, torch.ones(2, H, W) / 100)
-    ref32 = run_oracle(sc, cam, deg)
+    ref32 = run_oracle(sc, cam, deg, record=True)
     ref = run_oracle(sc, cam, deg, grads=grads, dtype=torch.float64, decisions=ref32["decisions"])
     cu = run_cuda(sc, cam, deg, grads=grads)
     check_images(cu, ref32)
@@ -298,7 +300,7 @@ def test_odd_point_counts_forward_backward(P):
     sc, cam, deg = U.make_inputs(P, 48, 48, seed=37 + P, exact_knn=False, scale_mul=3.0)
     g = torch.Generator().manual_seed(P)
     grads = (torch.randn(3, 48, 48, generator=g), torch.randn(2, 48, 48, generator=g))
-    ref32 = run_oracle(sc, cam, deg)
+    ref32 = run_oracle(sc, cam, deg, record=True)
     ref = run_oracle(sc, cam, deg, grads=grads, dtype=torch.float64, decisions=ref32["decisions"])
     cu = run_cuda(sc, cam, deg, grads=grads)
     check_images(cu, ref32)

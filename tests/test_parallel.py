@@ -22,7 +22,13 @@ def _gloo_worker(rank, world, port, q):
     from oracle import splat_ref as O
     from tests import util_scene as U
     torch.set_num_threads(2)
-    assert parallel.shard_views(5) == list(range(rank, 5, world))
+    assert parallel.shard_views(6) == list(range(rank, 6, world))
+    assert parallel.shard_views(5, allow_uneven=True) == list(range(rank, 5, world))
+    try:
+        parallel.shard_views(5)
+        uneven_refused = False
+    except ValueError:
+        uneven_refused = True
     parallel.enable_view_sharding()
     # each rank differentiates ITS view with the oracle; the reduced gradient must equal the
     # sequential two-view sum that DreamScene's loop produces (scene_trainer.py:801-829,881)
@@ -41,7 +47,25 @@ def _gloo_worker(rank, world, port, q):
     parallel.disable_view_sharding()
     untouched = grads[rank].clone()
     parallel.maybe_all_reduce(untouched)
-    ok = ok and torch.equal(untouched, grads[rank])
+    ok = ok and torch.equal(untouched, grads[rank]) and uneven_refused
+    # no_sync() suspends the in-backward reduction
+    parallel.enable_view_sharding()
+    with parallel.no_sync():
+        ok = ok and not parallel.reduction_active()
+        kept = grads[rank].clone()
+        parallel.maybe_all_reduce(kept)
+        ok = ok and torch.equal(kept, grads[rank])
+    ok = ok and parallel.reduction_active()
+    # DDP-style reduction of leaf gradients, with columns that are zero on every rank left out
+    parallel.enable_view_sharding(mode="deferred")
+    ok = ok and not parallel.reduction_active()
+    a = torch.nn.Parameter(torch.zeros(7, 3)); b = torch.nn.Parameter(torch.zeros(7, 15, 3)); c = torch.nn.Parameter(torch.zeros(4))
+    a.grad = torch.full((7, 3), float(rank + 1))
+    b.grad = torch.zeros(7, 15, 3); b.grad[:, :3] = float(10 * (rank + 1))
+    parallel.all_reduce_gradients([a, b, c], active_columns={b: 3})
+    ok = ok and torch.equal(a.grad, torch.full((7, 3), 3.0)) and c.grad is None
+    ok = ok and torch.equal(b.grad[:, :3], torch.full((7, 3, 3), 30.0)) and float(b.grad[:, 3:].abs().max()) == 0.0
+    parallel.disable_view_sharding()
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
@@ -60,32 +84,61 @@ def test_view_sharding_host_logic_gloo_world2():
 
 
 def _nccl_worker(rank, world, port, q):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      B200GSR_CHECK_COLLECTIVES="1")
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from dreamscene_b200 import GaussianRasterizer, parallel
     from tests import util_scene as U
-    sc, _, deg = U.make_inputs(20000, 256, 256, seed=23)
+    P = 20000
+    sc, _, _ = U.make_inputs(P, 256, 256, seed=23)
     dev = torch.device("cuda", rank)
+    names = ("means3D", "opacities", "shs", "scales", "rotations")
+    results = {}
 
-    def view_grads(view, reduce):
+    def view_grads(view, deg, mode, noise_seed=None):
+        """mode: 'backward' (in-backward chunked reduction), 'off' (no reduction), 'deferred' (leaf grads reduced
+        afterwards).  noise_seed: scene_render-style scale/SH augmentation between leaves and rasterizer."""
         cam = U.cameras.orbit_camera(phi_deg=45.0 * view, height=256, width=256)
         S = U.cuda_settings(cam, deg, device=dev)
         t = {k: v.to(dev).requires_grad_(True) for k, v in sc.items()}
-        m2d = torch.zeros(20000, 3, device=dev, requires_grad=True)
-        (parallel.enable_view_sharding if reduce else parallel.disable_view_sharding)()
+        m2d = torch.zeros(P, 3, device=dev, requires_grad=True)
+        if mode == "backward":
+            parallel.enable_view_sharding(chunks=3)
+        elif mode == "deferred":
+            parallel.enable_view_sharding(mode="deferred")
+        else:
+            parallel.disable_view_sharding()
+        shs, scales = t["shs"], t["scales"]
+        if noise_seed is not None:     # /root/reference/scene_gaussian.py:848-856
+            g = torch.Generator(device=dev).manual_seed(noise_seed)
+            shs = shs + torch.randn(shs.shape, generator=g, device=dev) * 0.05
+            scales = torch.clamp(scales + torch.randn(scales.shape, generator=g, device=dev) * 0.3 * scales, 0.0)
         color, radii, da = GaussianRasterizer(S)(means3D=t["means3D"], means2D=m2d, opacities=t["opacities"],
-                                                 shs=t["shs"], scales=t["scales"], rotations=t["rotations"])
+                                                 shs=shs, scales=scales, rotations=t["rotations"])
         (color.sum() + da.sum()).backward()
-        return torch.cat([t[k].grad.reshape(-1) for k in ("means3D", "opacities", "shs", "scales", "rotations")]), m2d.grad
+        if mode == "deferred":
+            ncoef = (deg + 1) ** 2
+            parallel.all_reduce_gradients([t[k] for k in names], active_columns={t["shs"]: ncoef})
+        return torch.cat([t[k].grad.reshape(-1) for k in names]), m2d.grad
 
-    reduced, m2d_own = view_grads(rank, True)                 # sharded: my view, all-reduced inside backward
-    seq = sum(view_grads(v, False)[0] for v in range(world))  # sequential loop on one GPU
-    err = float((reduced - seq).norm() / seq.norm())
-    own_only, m2d_seq = view_grads(rank, False)
-    # per-view means2D grads are NOT reduced (equal up to the fp32 atomic summation order)
-    ok = err < 1e-5 and float((m2d_own - m2d_seq).norm() / m2d_seq.norm()) < 1e-5
-    q.put((rank, ok, err))
+    ok = True
+    for deg in (3, 1, 0):       # degree < 3: only the active SH columns travel (compact payload)
+        reduced, m2d_own = view_grads(rank, deg, "backward")
+        seq = sum(view_grads(v, deg, "off")[0] for v in range(world))       # sequential loop on one GPU
+        err = float((reduced - seq).norm() / seq.norm())
+        _, m2d_seq = view_grads(rank, deg, "off")
+        # per-view means2D grads are NOT reduced (equal up to the fp32 atomic summation order)
+        ok = ok and err < 1e-5 and float((m2d_own - m2d_seq).norm() / m2d_seq.norm()) < 1e-5
+        results[f"backward_deg{deg}"] = err
+    # per-rank random augmentation between leaves and rasterizer: only the DDP-style reduction of the
+    # LEAF gradients reproduces the sequential sum (ADVICE r1)
+    red, _ = view_grads(rank, 1, "deferred", noise_seed=100 + rank)
+    seq = sum(view_grads(v, 1, "off", noise_seed=100 + v)[0] for v in range(world))
+    err = float((red - seq).norm() / seq.norm())
+    ok = ok and err < 1e-5
+    results["deferred_augmented"] = err
+    q.put((rank, ok, results))
     dist.destroy_process_group()
 
 
@@ -103,3 +156,14 @@ def test_view_sharded_backward_matches_sequential_sum_nccl():
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] for r in res), res
+
+
+def test_chunk_bounds_cover_the_range_with_aligned_starts():
+    from dreamscene_b200 import parallel
+    for P in (1, 127, 128, 129, 1000, 1_000_000, 2_627_680):
+        for chunks in (1, 3, 8):
+            b = parallel.chunk_bounds(P, chunks)
+            assert b[0][0] == 0 and b[-1][1] == P and len(b) <= chunks
+            assert all(g0 % 128 == 0 and g0 < g1 for g0, g1 in b)
+            assert all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
+    assert parallel.chunk_bounds(0) == []
