@@ -497,8 +497,8 @@ def main():
             floats = 3 + 1 + 3 * ncoef + 3 + 4
             line["limiting_collective"] = (
                 f"ncclAllReduce(SUM, fp32) of the parameter gradients: {floats} floats/Gaussian = {floats * 4 * P / 1e6:.0f} MB/step "
-                + ("in 8 coalesced chunks overlapped with project_bwd (inside backward)" if args.reduce == "backward"
-                   else "in one coalesced call on the leaf gradients after backward (DDP-style)"))
+                + ("one call on the rasterizer's flat gradient buffer, inside backward" if args.reduce == "backward"
+                   else "one call on the flattened leaf gradients after backward (DDP-style)"))
             line["reduce_mode"] = args.reduce
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_dict(wl, cpu_oracle_step(wl, 0))

@@ -22,7 +22,10 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dreamscene_b200 import GaussianRasterizationSettings, GaussianRasterizer  # noqa: E402
+from dreamscene_b200.postprocess import disparity_from_depth_alpha  # noqa: E402
+from dreamscene_b200.scene import assemble_scene  # noqa: E402
 from harness import cameras  # noqa: E402
+from harness.scene_ref import reference_assemble  # noqa: E402
 
 SH_C0 = 0.28209479177387814
 
@@ -76,34 +79,44 @@ def scene_camera(k, size, dev):
     return cameras.camera_from_pose(pose, 0.96, size, size, device=dev)
 
 
-def render(groups, cam, dev, bg, aug=True):
-    """scene_gaussian.py:673-893 restated."""
-    xyz = torch.cat([g["xyz"] for g in groups])
-    screenspace = torch.zeros_like(xyz, requires_grad=True) + 0
-    screenspace.retain_grad()
+def render(groups, cam, dev, bg, aug=True, glue="torch"):
+    """scene_gaussian.py:673-893 restated.  glue="torch": the reference's own PyTorch expressions
+    (per-group activations, torch.cat, augmentation); glue="fused" / "fused_rng": dreamscene_b200.scene
+    (one kernel each way; "fused_rng" also generates the noise in the kernel)."""
     S = GaussianRasterizationSettings(
         image_height=cam.image_height, image_width=cam.image_width, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
         bg=bg, scale_modifier=1.0, viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform,
         sh_degree=1, campos=cam.camera_center, prefiltered=False, score_flag=False)
-    opacity = torch.sigmoid(torch.cat([g["opacity"] for g in groups]))
-    scales = torch.exp(torch.cat([g["scaling"] for g in groups]))
-    rots = torch.nn.functional.normalize(torch.cat([g["rotation"] for g in groups]))
-    shs = torch.cat([torch.cat((g["f_dc"], g["f_rest"]), dim=1) for g in groups])
-    if aug:
-        shs = shs + torch.randn_like(shs) * 0.01                                   # :850-853
-        scales = torch.clamp(scales + torch.randn_like(scales) * 0.002, 0.0)       # :855-857 (exact zeros)
+    named = [{"_xyz": g["xyz"], "_opacity": g["opacity"], "_scaling": g["scaling"], "_rotation": g["rotation"],
+              "_features_dc": g["f_dc"], "_features_rest": g["f_rest"]} for g in groups]
+    if glue == "torch":
+        P = sum(g["xyz"].shape[0] for g in groups)
+        M = 1 + groups[0]["f_rest"].shape[1]
+        z_shs = torch.randn(P, M, 3, device=dev) if aug else None                   # :848-851
+        z_sc = torch.randn(P, 3, device=dev) if aug else None                       # :853-856 (exact zeros)
+        xyz, opacity, scales, rots, shs = reference_assemble(named, z_shs, z_sc)
+    else:
+        xyz, opacity, scales, rots, shs = assemble_scene(named, shs_aug=aug, scale_aug=aug,
+                                                         noise="torch" if glue == "fused" else "fused")
+    screenspace = torch.zeros_like(xyz, requires_grad=True) + 0
+    screenspace.retain_grad()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     image, radii, depth_alpha = GaussianRasterizer(S)(means3D=xyz, means2D=screenspace, shs=shs, colors_precomp=None,
                                                       opacities=opacity, scales=scales, rotations=rots,
                                                       cov3D_precomp=None)
     t1.record()
-    depth, alpha = torch.chunk(depth_alpha, 2)
     focal = 1 / (2 * math.tan(cam.FoVx / 2))
-    disp = focal / (depth + alpha * 10 + 1e-5)
-    m = alpha <= 0.1
-    min_d = disp[m].min() if bool(m.any()) else disp.min()
-    disp = torch.clamp((disp - min_d) / (disp.max() - min_d), 0.0, 1.0)
+    if glue == "torch":                                      # scene_gaussian.py:871-881 (one host sync per view)
+        depth, alpha = torch.chunk(depth_alpha, 2)
+        disp = focal / (depth + alpha * 10 + 1e-5)
+        try:
+            min_d = disp[alpha <= 0.1].min()
+        except Exception:
+            min_d = disp.min()
+        disp = torch.clamp((disp - min_d) / (disp.max() - min_d), 0.0, 1.0)
+    else:
+        disp, alpha = disparity_from_depth_alpha(depth_alpha, focal)
     return dict(image=image, depth=disp, alpha=alpha, radii=radii, viewspace=screenspace, ev=(t0, t1))
 
 
@@ -113,6 +126,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--views", type=int, default=4)
     ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--glue", default="torch", choices=["torch", "fused", "fused_rng"])
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
@@ -127,7 +141,7 @@ def main():
         for p in params:
             p.grad = None
         torch.cuda.synchronize(); t0 = time.perf_counter()
-        outs = [render(groups, scene_camera(it * a.views + k, a.size, dev), dev, bg) for k in range(a.views)]
+        outs = [render(groups, scene_camera(it * a.views + k, a.size, dev), dev, bg, glue=a.glue) for k in range(a.views)]
         images = torch.stack([o["image"] for o in outs]); depths = torch.stack([o["depth"] for o in outs])
         loss = ((images - target) ** 2).mean() * 100 + depths.mean() * 0.1      # SDS -> L2 stub (+ depth path)
         loss.backward()
@@ -138,7 +152,7 @@ def main():
             vis.append(float(np.mean([(o["radii"] > 0).float().mean().item() for o in outs])))
             pairs.append(R.last_pair_count(dev))
     finite = all(torch.isfinite(p.grad).all().item() for p in params)
-    print(json.dumps({"config": "cfg5_scene_step (re-enactment)", "P": P, "views": a.views, "size": a.size,
+    print(json.dumps({"config": "cfg5_scene_step (re-enactment)", "glue": a.glue, "P": P, "views": a.views, "size": a.size,
                       "M": 4, "sh_degree": 1, "step_ms": 1e3 * float(np.median(times)),
                       "rasterizer_fwd_ms_per_step": float(np.median(ras_fwd)),
                       "visible_fraction": float(np.mean(vis)), "tile_pairs_last_view": int(np.median(pairs)),

@@ -11,7 +11,9 @@ LIB_PATH = os.environ.get("B200GSR_LIB", os.path.join(HERE, "libb200gsr.so"))   
 EXPORTS = ["b200gsr_version", "b200gsr_last_error", "b200gsr_saved_layout_query",
            "b200gsr_scratch_layout_query", "b200gsr_forward", "b200gsr_backward", "b200gsr_backward_ex",
            "b200gsr_mark_visible", "b200gsr_profile_enable", "b200gsr_profile_counts",
-           "b200gsr_profile_read", "b200gsr_debug_counters", "b200gsr_dist2_scratch_bytes", "b200gsr_dist2_knn3"]
+           "b200gsr_profile_read", "b200gsr_debug_counters", "b200gsr_dist2_scratch_bytes", "b200gsr_dist2_knn3",
+           "b200gsr_assemble_forward", "b200gsr_assemble_backward", "b200gsr_disparity_forward",
+           "b200gsr_disparity_backward"]
 
 
 class Params(C.Structure):
@@ -21,6 +23,17 @@ class Params(C.Structure):
                 ("prefiltered", C.c_int32), ("score_flag", C.c_int32),
                 ("bg", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p),
                 ("campos", C.c_void_p)]
+
+
+class Group(C.Structure):           # == b200gsr_group
+    _fields_ = [(n, C.c_void_p) for n in ("xyz", "opacity", "scaling", "rotation", "f_dc", "f_rest")] + [("n", C.c_int32)]
+
+
+class GroupGrad(C.Structure):       # == b200gsr_group_grad
+    _fields_ = [(n, C.c_void_p) for n in ("xyz", "opacity", "scaling", "rotation", "f_dc", "f_rest")]
+
+
+MAX_GROUPS = 24
 
 
 class SavedLayout(C.Structure):
@@ -73,6 +86,13 @@ def load():
     lib.b200gsr_dist2_scratch_bytes.restype = C.c_size_t
     lib.b200gsr_dist2_knn3.argtypes = [i32, vp, vp, vp, sz, vp]
     lib.b200gsr_dist2_knn3.restype = C.c_int
+    lib.b200gsr_assemble_forward.argtypes = [i32, C.POINTER(Group), i32, C.c_float, C.c_float, vp, vp, u64] + [vp] * 5 + [vp]
+    lib.b200gsr_assemble_backward.argtypes = [i32, C.POINTER(Group), C.POINTER(GroupGrad), i32, C.c_float, C.c_float,
+                                              vp, vp, u64] + [vp] * 5 + [vp]
+    lib.b200gsr_assemble_forward.restype = lib.b200gsr_assemble_backward.restype = C.c_int
+    lib.b200gsr_disparity_forward.argtypes = [i32, i32, vp, vp, vp, vp, vp]
+    lib.b200gsr_disparity_backward.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.b200gsr_disparity_forward.restype = lib.b200gsr_disparity_backward.restype = C.c_int
     lib.b200gsr_debug_counters.argtypes = [vp]
     lib.b200gsr_debug_counters.restype = C.c_int
     lib.b200gsr_profile_enable.argtypes = [i32]

@@ -353,6 +353,81 @@ int b200gsr_profile_read(int32_t is_backward, int32_t call, float* ms) {
     return B200GSR_OK;
 }
 
+static int check_groups(int32_t num_groups, const b200gsr_group* groups, int32_t M) {
+    if (num_groups < 0 || num_groups > B200GSR_MAX_GROUPS) return fail(B200GSR_ERR_UNSUPPORTED, "num_groups %d not in 0..%d", num_groups, B200GSR_MAX_GROUPS);
+    if (num_groups > 0 && !groups) return fail(B200GSR_ERR_BAD_ARG, "groups is null");
+    if (M < 1 || M > 16) return fail(B200GSR_ERR_BAD_ARG, "M=%d not in 1..16", M);
+    long long total = 0;
+    for (int g = 0; g < num_groups; ++g) {
+        const b200gsr_group& gr = groups[g];
+        if (gr.n < 0) return fail(B200GSR_ERR_BAD_ARG, "group %d: negative size", g);
+        if (gr.n > 0 && (!gr.xyz || !gr.opacity || !gr.scaling || !gr.rotation || !gr.f_dc || (M > 1 && !gr.f_rest)))
+            return fail(B200GSR_ERR_BAD_ARG, "group %d: null parameter pointer", g);
+        if (gr.n > 0 && (reinterpret_cast<uintptr_t>(gr.rotation) & 15u))
+            return fail(B200GSR_ERR_BAD_ARG, "group %d: rotation must be 16-byte aligned", g);
+        total += gr.n;
+    }
+    if (total > 0x7fffffffLL) return fail(B200GSR_ERR_UNSUPPORTED, "more than 2^31-1 Gaussians");
+    return B200GSR_OK;
+}
+
+int b200gsr_assemble_forward(int32_t num_groups, const b200gsr_group* groups, int32_t M, float shs_noise,
+                             float scale_noise, const float* z_shs, const float* z_scales, uint64_t seed,
+                             float* means3D, float* opacities, float* scales, float* rotations, float* shs,
+                             void* stream) {
+    int rc = check_groups(num_groups, groups, M);
+    if (rc) return rc;
+    if (!means3D || !opacities || !scales || !rotations || !shs) return fail(B200GSR_ERR_BAD_ARG, "null output pointer");
+    GSR_RANGE_PUSH("b200gsr.assemble_fwd");
+    rc = check_cuda(gsr_launch_assemble(false, num_groups, groups, nullptr, M, shs_noise, scale_noise, z_shs, z_scales,
+                                        seed, means3D, opacities, scales, rotations, shs,
+                                        static_cast<cudaStream_t>(stream)), "assemble_forward");
+    GSR_RANGE_POP();
+    return rc;
+}
+
+int b200gsr_assemble_backward(int32_t num_groups, const b200gsr_group* groups, const b200gsr_group_grad* grads,
+                              int32_t M, float shs_noise, float scale_noise, const float* z_shs,
+                              const float* z_scales, uint64_t seed, const float* d_means3D,
+                              const float* d_opacities, const float* d_scales, const float* d_rotations,
+                              const float* d_shs, void* stream) {
+    int rc = check_groups(num_groups, groups, M);
+    if (rc) return rc;
+    if (num_groups > 0 && !grads) return fail(B200GSR_ERR_BAD_ARG, "grads is null");
+    for (int g = 0; g < num_groups; ++g)
+        if (groups[g].n > 0 && (!grads[g].xyz || !grads[g].opacity || !grads[g].scaling || !grads[g].rotation ||
+                                !grads[g].f_dc || (M > 1 && !grads[g].f_rest)))
+            return fail(B200GSR_ERR_BAD_ARG, "group %d: null gradient pointer", g);
+    if (!d_means3D || !d_opacities || !d_scales || !d_rotations || !d_shs) return fail(B200GSR_ERR_BAD_ARG, "null gradient input");
+    GSR_RANGE_PUSH("b200gsr.assemble_bwd");
+    rc = check_cuda(gsr_launch_assemble(true, num_groups, groups, grads, M, shs_noise, scale_noise, z_shs, z_scales, seed,
+                                        const_cast<float*>(d_means3D), const_cast<float*>(d_opacities),
+                                        const_cast<float*>(d_scales), const_cast<float*>(d_rotations),
+                                        const_cast<float*>(d_shs), static_cast<cudaStream_t>(stream)), "assemble_backward");
+    GSR_RANGE_POP();
+    return rc;
+}
+
+int b200gsr_disparity_forward(int32_t B, int32_t N, const float* depth_alpha, const float* focal, float* out_disp,
+                              void* stats, void* stream) {
+    if (B < 0 || N < 0 || ((B > 0 && N > 0) && (!depth_alpha || !focal || !out_disp || !stats)))
+        return fail(B200GSR_ERR_BAD_ARG, "bad disparity_forward arguments");
+    DeviceState* ds = device_state();
+    if (!ds) return fail(B200GSR_ERR_CUDA, "cannot query the current CUDA device");
+    return check_cuda(gsr_launch_disparity_fwd(B, N, depth_alpha, focal, out_disp, stats, ds->num_sms,
+                                               static_cast<cudaStream_t>(stream)), "disparity_forward");
+}
+
+int b200gsr_disparity_backward(int32_t B, int32_t N, const float* depth_alpha, const float* focal, const float* g_disp,
+                               const float* g_alpha, void* stats, float* d_depth_alpha, void* stream) {
+    if (B < 0 || N < 0 || ((B > 0 && N > 0) && (!depth_alpha || !focal || !g_disp || !stats || !d_depth_alpha)))
+        return fail(B200GSR_ERR_BAD_ARG, "bad disparity_backward arguments");
+    DeviceState* ds = device_state();
+    if (!ds) return fail(B200GSR_ERR_CUDA, "cannot query the current CUDA device");
+    return check_cuda(gsr_launch_disparity_bwd(B, N, depth_alpha, focal, g_disp, g_alpha, stats, d_depth_alpha,
+                                               ds->num_sms, static_cast<cudaStream_t>(stream)), "disparity_backward");
+}
+
 int b200gsr_debug_counters(unsigned long long* device_counters) {
     g_stats = device_counters;
     return B200GSR_OK;

@@ -188,6 +188,18 @@ cudaError_t gsr_launch_project_bwd(const GsrBwdArgs& a);
 cudaError_t gsr_launch_mark_visible(int P, const float* means3D, const float* view,
                                     const float* proj, uint8_t* visible, cudaStream_t s);
 
+// scene assembly (assemble.cu)
+cudaError_t gsr_launch_assemble(bool backward, int num_groups, const b200gsr_group* groups,
+                                const b200gsr_group_grad* grads, int M, float c_shs, float c_scale,
+                                const float* z_shs, const float* z_scales, unsigned long long seed,
+                                float* means3D, float* opac, float* scales, float* rots, float* shs, cudaStream_t s);
+
+// disparity post-processing (postprocess.cu)
+cudaError_t gsr_launch_disparity_fwd(int B, int N, const float* da, const float* focal, float* out, void* stats,
+                                     int num_sms, cudaStream_t s);
+cudaError_t gsr_launch_disparity_bwd(int B, int N, const float* da, const float* focal, const float* g_out,
+                                     const float* g_alpha, void* stats, float* d_da, int num_sms, cudaStream_t s);
+
 // simple_knn replacement (knn.cu)
 size_t gsr_knn_scratch_bytes(int P, int* max_cells_out);
 cudaError_t gsr_launch_knn(int P, const float* pts, float* out, uint8_t* scratch, cudaStream_t s);

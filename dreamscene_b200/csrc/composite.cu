@@ -19,8 +19,10 @@
 //   * backward: per-(warp, Gaussian) partial gradients are reduced with a halving shuffle
 //     butterfly (12 SHFL for 10 values) and committed with ONE coalesced RED instruction.
 #include "common.cuh"
+#include <cuda.h>          // CUtensorMap types only; the encoder is fetched with cudaGetDriverEntryPoint
 #include <cuda_fp16.h>
 #include <cstdlib>
+#include <cstring>
 
 namespace {
 
@@ -269,6 +271,212 @@ composite_fwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restric
         if (lane == 0) {
             atomicAdd(stats + GSR_STAT_FWD_EVAL, (unsigned long long)st_eval);
             atomicAdd(stats + GSR_STAT_FWD_LANES, (unsigned long long)tl);
+        }
+    }
+}
+
+// =============================================================================================
+// Forward, Blackwell bulk-copy staging variants (A/B experiment for the north star's
+// "TMA/cp.async.bulk staging of per-tile Gaussian blocks"; profiles/r02_tma_ab.md):
+//   FWD_VARIANT 1: the tile's KEY chunks are staged with cp.async.bulk (UBLKCP) + mbarrier into a
+//                  3-deep shared-memory ring by one elected thread; records still move with LDGSTS;
+//   FWD_VARIANT 2: additionally the RECORDS are fetched with Blackwell's row-gather TMA,
+//                  cp.async.bulk.tensor.2d...tile::gather4 over geom viewed as f32[P][12]: one
+//                  instruction per 4 records (64 per chunk) instead of 768 LDGSTS.
+// Key chunks start at an arbitrary pair offset (8-byte granularity); bulk copies need 16-byte
+// aligned sources, so the copy starts at the even pair index at or below the chunk start and is
+// two keys longer (the key array has two spare entries at its end for exactly this).
+// =============================================================================================
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_gather4(void* dst, const void* tmap, int col, int r0, int r1, int r2, int r3,
+                                            unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes "
+                 "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                 :: "r"(smem_u32(dst)), "l"(tmap), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct __align__(128) TmaMap { unsigned char bytes[128]; };   // CUtensorMap (opaque here)
+
+constexpr int kQuadF4 = 16;     // VARIANT 2: 4 records (12 float4) padded to 256 B so every gather4 lands 128-B aligned
+struct __align__(128) SmemFwdTma {
+    float4 rec[2][kChunk * 4];                       // VARIANT 1 uses [kChunk*3] of it (48-B records)
+    unsigned long long keys[3][kChunk + 2];
+    unsigned long long kbar[3];
+    unsigned long long rbar[2];
+    uint32_t work;
+};
+
+template <int VARIANT>
+__global__ void __launch_bounds__(256)
+composite_fwd_tma_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restrict__ header,
+                         const uint32_t* __restrict__ work_order,
+                         const uint32_t* __restrict__ tile_start,
+                         const unsigned long long* __restrict__ keys, const GsrRec* __restrict__ geom,
+                         const __grid_constant__ TmaMap tmap,
+                         const float* __restrict__ bg, uint32_t* __restrict__ queue,
+                         float* __restrict__ out_color, float* __restrict__ out_depth_alpha,
+                         uint32_t* __restrict__ n_contrib) {
+    constexpr int kThreads = 256;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SmemFwdTma& sm = *reinterpret_cast<SmemFwdTma*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t max_pairs = header[GSR_H_MAX_PAIRS];
+    const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) mbar_init(&sm.kbar[i], 1);
+        for (int i = 0; i < 2; ++i) mbar_init(&sm.rbar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t kphase = 0, rphase = 0;    // bit i = parity of the NEXT completion to wait for on barrier i
+
+    for (;;) {
+        if (tid == 0) sm.work = atomicAdd(queue, 1u);
+        __syncthreads();
+        const uint32_t w = sm.work;
+        __syncthreads();
+        if (w >= (uint32_t)ntiles) break;
+        const uint32_t tile = work_order[w];
+        uint32_t beg = tile_start[tile], end = tile_start[tile + 1];
+        if (end > max_pairs) end = max_pairs;
+        if (beg > end) beg = end;
+        const int n = (int)(end - beg);
+        const int nchunks = (n + kChunk - 1) / kChunk;
+        const int odd = (int)(beg & 1u);                       // 16-B alignment slack of this tile's key range
+        const unsigned long long* tk16 = keys + (beg - odd);   // even pair index: 16-byte aligned
+        const int tyi = tile / gx, txi = tile - tyi * gx;
+        const int X0i = txi * GSR_TILE + (wid & 1) * 8, Y0i = tyi * GSR_TILE + (wid >> 1) * 4;
+        const int Xi = X0i + (lane & 7), Yi = Y0i + (lane >> 3);
+        const float X0 = (float)X0i, Y0 = (float)Y0i, X = (float)Xi, Y = (float)Yi;
+        const bool inside = Xi < W && Yi < H;
+        bool done = !inside;
+        float T = 1.0f, Cr = 0.f, Cg = 0.f, Cb = 0.f, Dacc = 0.f;
+        uint32_t last = 0;
+
+        // issue the bulk copy of key chunk c into ring slot c % 3 (one elected thread)
+        auto issue_keys = [&](int c) {
+            if (tid == 0 && c < nchunks) {
+                const uint32_t bytes = (uint32_t)((kChunk + 2) * sizeof(unsigned long long));
+                mbar_expect_tx(&sm.kbar[c % 3], bytes);
+                bulk_g2s(sm.keys[c % 3], tk16 + (size_t)c * kChunk, bytes, &sm.kbar[c % 3]);
+            }
+        };
+        auto wait_keys = [&](int c) {
+            mbar_wait(&sm.kbar[c % 3], (kphase >> (c % 3)) & 1u);
+            kphase ^= 1u << (c % 3);
+        };
+        // gather the records of chunk c (keys already in shared memory) into record buffer c & 1
+        auto issue_records = [&](int c) {
+            const int cnt = min(kChunk, n - c * kChunk);
+            const unsigned long long* sk = sm.keys[c % 3] + odd;
+            if (VARIANT == 2) {
+                const int nq = (cnt + 3) >> 2;
+                if (tid == 0) mbar_expect_tx(&sm.rbar[c & 1], (uint32_t)nq * 4u * 48u);
+                __syncwarp();
+                if (tid < nq) {
+                    int r[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) r[j] = (4 * tid + j < cnt) ? (int)(uint32_t)sk[4 * tid + j] : 0;
+                    tma_gather4(&sm.rec[c & 1][tid * kQuadF4], &tmap, 0, r[0], r[1], r[2], r[3], &sm.rbar[c & 1]);
+                }
+            } else {
+                if (tid < cnt) gather_record(reinterpret_cast<GsrRec*>(sm.rec[c & 1]) + tid, geom, sk[tid]);
+                cp_async_commit();
+            }
+        };
+        auto wait_records = [&](int c) {
+            if (VARIANT == 2) {
+                mbar_wait(&sm.rbar[c & 1], (rphase >> (c & 1)) & 1u);
+                rphase ^= 1u << (c & 1);
+            } else {
+                cp_async_wait<0>();
+            }
+        };
+
+        int keys_issued = 0, keys_waited = 0, recs_issued = 0, recs_waited = 0;
+        if (nchunks > 0) {
+            issue_keys(0); issue_keys(1); keys_issued = min(2, nchunks);
+            wait_keys(0); keys_waited = 1;
+            issue_records(0); recs_issued = 1;
+        }
+        for (int c = 0; c < nchunks; ++c) {
+            wait_records(c); recs_waited = c + 1;
+            // everyone's view of chunk c is complete, everyone is done with chunk c-1 (its record buffer
+            // and the key slot (c+2) % 3 == (c-1) % 3 are free); doubles as the CTA-wide early-out vote
+            const int ndone = __syncthreads_count(done);
+            if (ndone == kThreads) break;
+            if (c + 2 < nchunks) { issue_keys(c + 2); keys_issued = c + 3; }
+            if (c + 1 < nchunks) {
+                wait_keys(c + 1); keys_waited = c + 2;
+                issue_records(c + 1); recs_issued = c + 2;
+            }
+            const int cnt = min(kChunk, n - c * kChunk);
+            if (__all_sync(0xffffffffu, done)) continue;   // this warp is saturated
+            for (int sub = 0; sub * 32 < cnt; ++sub) {
+                const int r = sub * 32 + lane;
+                bool pass = false;
+                if (r < cnt) {
+                    const float4 q0 = (VARIANT == 2) ? sm.rec[c & 1][(r >> 2) * kQuadF4 + (r & 3) * 3] : sm.rec[c & 1][3 * r];
+                    pass = cull_pass(q0.x, q0.y, __float_as_uint(q0.z), X0, Y0);
+                }
+                uint32_t mask = __ballot_sync(0xffffffffu, pass);
+                const uint32_t pos0 = (uint32_t)(c * kChunk + sub * 32 + 1);
+                while (mask) {
+                    const int b = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int e = sub * 32 + b;
+                    const float4* rp = (VARIANT == 2) ? &sm.rec[c & 1][(e >> 2) * kQuadF4 + (e & 3) * 3] : &sm.rec[c & 1][3 * e];
+                    const float4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
+                    const PairEval ev = eval_pair(q0.x, q0.y, q0.w, q1.x, q1.y, q1.z, X, Y);
+                    if (ev.valid && !done) {
+                        const float Tn = T * (1.0f - ev.alpha);
+                        if (Tn < GSR_T_STOP) {
+                            done = true;
+                        } else {
+                            const float wgt = ev.alpha * T;
+                            Cr = fmaf(q2.x, wgt, Cr); Cg = fmaf(q2.y, wgt, Cg); Cb = fmaf(q2.z, wgt, Cb);
+                            Dacc = fmaf(q1.w, wgt, Dacc);
+                            T = Tn;
+                            last = pos0 + (uint32_t)b;
+                        }
+                    }
+                }
+                if (__all_sync(0xffffffffu, done)) break;
+            }
+        }
+        // never leave bulk copies in flight across tiles (early-out case): drain what was issued
+        while (recs_waited < recs_issued) { wait_records(recs_waited); ++recs_waited; }
+        while (keys_waited < keys_issued) { wait_keys(keys_waited); ++keys_waited; }
+        __syncthreads();
+
+        if (inside) {
+            const size_t plane = (size_t)H * W;
+            const size_t pix = (size_t)Yi * W + Xi;
+            out_color[pix] = fmaf(T, bg0, Cr);
+            out_color[plane + pix] = fmaf(T, bg1, Cg);
+            out_color[2 * plane + pix] = fmaf(T, bg2, Cb);
+            out_depth_alpha[pix] = Dacc;
+            out_depth_alpha[plane + pix] = T;
+            n_contrib[pix] = last;
         }
     }
 }
@@ -701,11 +909,56 @@ static cudaError_t launch_fwd(const GsrFwdArgs& a, int nblocks, const CompPtrs& 
     return cudaGetLastError();
 }
 
+// ---- tensor map for the gather4 variant: geom viewed as f32[P][12], box = one 48-byte row ------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static cudaError_t make_geom_tensor_map(const GsrRec* geom, int P, TmaMap* out) {
+    static EncodeTiledFn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) fn = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(fn);
+    }();
+    if (!encode) return cudaErrorNotSupported;
+    static_assert(sizeof(CUtensorMap) == sizeof(TmaMap), "tensor map size");
+    const cuuint64_t dims[2] = {12, (cuuint64_t)(P > 0 ? P : 1)};
+    const cuuint64_t strides[1] = {sizeof(GsrRec)};
+    const cuuint32_t box[2] = {12, 1};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                        const_cast<GsrRec*>(geom), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+template <int VARIANT>
+static cudaError_t launch_fwd_tma(const GsrFwdArgs& a, int nblocks, const CompPtrs& c, uint32_t* queue) {
+    const int smem = (int)sizeof(SmemFwdTma);
+    static std::atomic<unsigned long long> attr_done{0};
+    cudaError_t e = gsr_smem_once(composite_fwd_tma_kernel<VARIANT>, smem, attr_done);
+    if (e != cudaSuccess) return e;
+    TmaMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (VARIANT == 2 && (e = make_geom_tensor_map(c.geom, a.prm.P, &tmap)) != cudaSuccess) return e;
+    composite_fwd_tma_kernel<VARIANT><<<nblocks, 256, smem, a.stream>>>(
+        a.prm.image_height, a.prm.image_width, c.grid.gx, c.grid.ntiles, c.header, c.work_order, c.tile_start,
+        c.keys, c.geom, tmap, a.prm.bg, queue, a.out_color, a.out_depth_alpha, c.n_contrib);
+    return cudaGetLastError();
+}
+
 cudaError_t gsr_launch_composite_fwd(const GsrFwdArgs& a) {
     const CompPtrs c = comp_ptrs(a.saved, a.vl, a.prm.image_height, a.prm.image_width);
     if (c.grid.ntiles == 0) return cudaSuccess;
     uint32_t* queue = reinterpret_cast<uint32_t*>(a.scratch + a.sl.counters) + GSR_C_FWD_QUEUE;
     const int nblocks = min(c.grid.ntiles, a.num_sms * 6);
+    // B200GSR_FWD_VARIANT = 1 | 2: bulk-copy / TMA staging experiments (profiles/r02_tma_ab.md)
+    static const int fwd_variant = [] { const char* e = getenv("B200GSR_FWD_VARIANT"); return e ? atoi(e) : 0; }();
+    if (fwd_variant != 0 && !a.prm.score_flag && a.stats == nullptr) {
+        const int nb = min(c.grid.ntiles, a.num_sms * 5);
+        return fwd_variant == 2 ? launch_fwd_tma<2>(a, nb, c, queue) : launch_fwd_tma<1>(a, nb, c, queue);
+    }
     if (a.stats != nullptr)
         return a.prm.score_flag ? launch_fwd<true, true>(a, nblocks, c, queue) : launch_fwd<false, true>(a, nblocks, c, queue);
     return a.prm.score_flag ? launch_fwd<true, false>(a, nblocks, c, queue) : launch_fwd<false, false>(a, nblocks, c, queue);

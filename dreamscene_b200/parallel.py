@@ -14,9 +14,12 @@ are summed over NCCL/NVLink.  Two ways to do the sum, both additive to the refer
    /root/reference/training/object_trainer.py:243-244) can be left out of the payload.
 
 2. ``enable_view_sharding(mode="backward")``: the rasterizer's backward all-reduces its flat
-   parameter-gradient buffer itself, chunk by chunk, overlapping the reduction of finished chunks
-   with the per-Gaussian backward of the remaining ones, and sends only the active degree's SH
-   columns.  This reduces the gradient AT THE RASTERIZER INPUTS, so it equals the sequential sum
+   parameter-gradient buffer itself (ONE ncclAllReduce, no staging copy) and sends only the active
+   degree's SH columns.  ``chunks=K > 1`` pipelines the reduction over K Gaussian ranges, overlapping
+   finished chunks with the per-Gaussian backward of the rest; measured on 4 x B200 this LOSES
+   (1.82 vs 1.44 ms/step at K=8: 40 small collectives cost more than the 0.14 ms of project_bwd they
+   can hide; profiles/r02_scale_probe.md), so the default is K=1.
+   This mode reduces the gradient AT THE RASTERIZER INPUTS, so it equals the sequential sum
    only when the map parameters -> rasterizer inputs is the same deterministic function on every
    rank (inputs are leaves, or activations without per-rank randomness).  Every rank must issue the
    same sequence of rasterizer backward calls with the same P; set B200GSR_CHECK_COLLECTIVES=1 to
@@ -37,12 +40,12 @@ import torch.distributed as dist
 
 _group = None
 _enabled = False
-_chunks = 8
+_chunks = 1
 _suspended = 0
 _CHECK = bool(int(os.environ.get("B200GSR_CHECK_COLLECTIVES", "0")))
 
 
-def enable_view_sharding(group: Optional["dist.ProcessGroup"] = None, mode: str = "backward", chunks: int = 8) -> None:
+def enable_view_sharding(group: Optional["dist.ProcessGroup"] = None, mode: str = "backward", chunks: int = 1) -> None:
     """mode="backward": every rasterizer backward all-reduces its parameter gradients (see the module
     docstring for when that is exact); mode="deferred": nothing happens inside backward, call
     all_reduce_gradients() yourself.  `chunks` = number of Gaussian ranges the in-backward
@@ -167,7 +170,16 @@ def all_reduce_gradients(params: Iterable[torch.Tensor], group: Optional["dist.P
             jobs.append((g, g.contiguous()))
     if not jobs:
         return
-    _coalesced_all_reduce([t for _, t in jobs], group, async_ops=False)
+    tensors = [t for _, t in jobs]
+    total = sum(t.numel() for t in tensors)
+    if len(tensors) > 1 and total >= (1 << 20) and all(t.dtype == tensors[0].dtype for t in tensors):
+        # one big message beats a group of medium ones (measured 4 x B200, 236 MB: 0.60 ms flat vs
+        # 0.80 ms as five coalesced tensors): stage through a flat buffer (2 extra HBM passes, ~0.1 ms)
+        flat = torch.cat([t.reshape(-1) for t in tensors])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        torch._foreach_copy_([t.reshape(-1) for t in tensors], list(flat.split([t.numel() for t in tensors])))
+    else:
+        _coalesced_all_reduce(tensors, group, async_ops=False)
     for dst, t in jobs:
         if dst is not None:
             dst.copy_(t)

@@ -422,13 +422,17 @@ class _RasterizeGaussians(torch.autograd.Function):
                     if rc:
                         raise RuntimeError(f"b200gsr_backward failed ({rc}): {_lib.last_error()}")
 
+                bounds = _parallel.chunk_bounds(P) if reduce else []
                 if not reduce:
                     launch(_lib.BWD_COMPOSITE | _lib.BWD_PROJECT, 0, P)
+                elif len(bounds) <= 1:
+                    launch(_lib.BWD_COMPOSITE | _lib.BWD_PROJECT, 0, P)
+                    _parallel.maybe_all_reduce(flat[:o] if o > 0 else flat)      # ONE ncclAllReduce of the flat buffer
                 else:
                     red = _parallel.ChunkReducer(flat.numel(), dev)
                     launch(_lib.BWD_COMPOSITE, 0, 0)
                     names = [k for k in ("means3D", "opac", "col", "scales", "rots", "cov") if k in offs]
-                    for g0, g1 in _parallel.chunk_bounds(P):
+                    for g0, g1 in bounds:
                         launch(_lib.BWD_PROJECT, g0, g1)
                         red.reduce([sec(k, g0, g1) for k in names])
                     red.wait()

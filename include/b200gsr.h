@@ -185,6 +185,55 @@ int b200gsr_mark_visible(int32_t P, const float* means3D, const float* viewmatri
                          const float* projmatrix, uint8_t* visible, void* stream);
 
 /*
+ * scene assembly = activations + group concatenation + augmentation noise of
+ * scene_render (/root/reference/scene_gaussian.py:753-857; gs_renderer.py:464-488) as one kernel,
+ * and its backward as one kernel.  `groups` is a HOST array of `num_groups` (<= B200GSR_MAX_GROUPS)
+ * entries holding DEVICE pointers to each group's raw leaf parameters
+ *   xyz[n,3] opacity[n,1] scaling[n,3] rotation[n,4] (16-byte aligned) f_dc[n,1,3] f_rest[n,M-1,3]
+ * Outputs are the packed rasterizer inputs for P = sum n rows:
+ *   means3D[P,3] = xyz, opacities[P,1] = sigmoid, scales[P,3] = exp (+ noise, clamped at 0),
+ *   rotations[P,4] = q / max(|q|, 1e-12), shs[P,M,3] = cat(f_dc, f_rest) (+ noise).
+ * Noise (reference: v + randn * (0.2**0.5 * v [/ 4 for scales])): shs_noise / scale_noise are the
+ * coefficients (0 = off, reference value 0.2**0.5); z_shs[P,M,3] / z_scales[P,3] are standard-normal
+ * draws supplied by the caller (same tensors in forward and backward), or NULL to generate them in
+ * the kernel from `seed` (counter-based Philox4x32-10; nothing is stored, backward regenerates).
+ * Backward: d_* are the gradients w.r.t. the packed outputs, `grads` the per-group destinations
+ * (same shapes as the raw parameters, fully overwritten).
+ */
+#define B200GSR_MAX_GROUPS 24
+typedef struct b200gsr_group {
+    const float *xyz, *opacity, *scaling, *rotation, *f_dc, *f_rest;
+    int32_t n;
+} b200gsr_group;
+typedef struct b200gsr_group_grad {
+    float *xyz, *opacity, *scaling, *rotation, *f_dc, *f_rest;
+} b200gsr_group_grad;
+int b200gsr_assemble_forward(int32_t num_groups, const b200gsr_group* groups, int32_t M,
+                             float shs_noise, float scale_noise, const float* z_shs, const float* z_scales,
+                             uint64_t seed, float* means3D, float* opacities, float* scales, float* rotations,
+                             float* shs, void* stream);
+int b200gsr_assemble_backward(int32_t num_groups, const b200gsr_group* groups, const b200gsr_group_grad* grads,
+                              int32_t M, float shs_noise, float scale_noise, const float* z_shs,
+                              const float* z_scales, uint64_t seed, const float* d_means3D,
+                              const float* d_opacities, const float* d_scales, const float* d_rotations,
+                              const float* d_shs, void* stream);
+
+/*
+ * SURVEY.md 8(f1, post-processing half): depth/alpha -> normalised disparity of
+ * /root/reference/scene_gaussian.py:871-881 for a batch of B views without any host synchronisation.
+ *   depth_alpha [B,2,N] (N = H*W; channel 1 = transmittance), focal [B] (device), out_disp [B,N],
+ *   stats = 32*B bytes of device scratch that must be kept for the backward.
+ * Backward: g_disp [B,N] = dL/d out_disp, g_alpha [B,N] or NULL = dL/d alpha from other consumers of the
+ * alpha channel; d_depth_alpha [B,2,N] is fully overwritten.  `stats` is updated in place (pass a copy
+ * of the forward's record if the backward may run more than once).
+ */
+int b200gsr_disparity_forward(int32_t B, int32_t N, const float* depth_alpha, const float* focal,
+                              float* out_disp, void* stats, void* stream);
+int b200gsr_disparity_backward(int32_t B, int32_t N, const float* depth_alpha, const float* focal,
+                               const float* g_disp, const float* g_alpha, void* stats,
+                               float* d_depth_alpha, void* stream);
+
+/*
  * replaces simple_knn._C.distCUDA2 (un-vendored; /root/reference/gs_renderer.py:9,590-593):
  * out[i] = mean of the squared distances from points[i] to its 3 nearest OTHER points (points f32[P,3]).
  * `scratch` = b200gsr_dist2_scratch_bytes(P) bytes of device memory.
