@@ -13,7 +13,9 @@ EXPORTS = ["b200gsr_version", "b200gsr_last_error", "b200gsr_saved_layout_query"
            "b200gsr_mark_visible", "b200gsr_profile_enable", "b200gsr_profile_counts",
            "b200gsr_profile_read", "b200gsr_debug_counters", "b200gsr_dist2_scratch_bytes", "b200gsr_dist2_knn3",
            "b200gsr_assemble_forward", "b200gsr_assemble_backward", "b200gsr_disparity_forward",
-           "b200gsr_disparity_backward"]
+           "b200gsr_disparity_backward", "b200gsr_densify_stats", "b200gsr_densify_scratch_bytes",
+           "b200gsr_densify_plan", "b200gsr_densify_map", "b200gsr_compact_plan", "b200gsr_gather_rows",
+           "b200gsr_split_children", "b200gsr_kth_smallest"]
 
 
 class Params(C.Structure):
@@ -93,6 +95,19 @@ def load():
     lib.b200gsr_disparity_forward.argtypes = [i32, i32, vp, vp, vp, vp, vp]
     lib.b200gsr_disparity_backward.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.b200gsr_disparity_forward.restype = lib.b200gsr_disparity_backward.restype = C.c_int
+    f = C.c_float
+    lib.b200gsr_densify_stats.argtypes = [i32, vp, vp, vp, vp, vp, vp]
+    lib.b200gsr_densify_scratch_bytes.argtypes = [i32]
+    lib.b200gsr_densify_scratch_bytes.restype = C.c_size_t
+    lib.b200gsr_densify_plan.argtypes = [i32, vp, vp, vp, vp, f, f, f, f, f, vp, vp, vp]
+    lib.b200gsr_densify_map.argtypes = [i32, i32, vp, vp, vp, vp, vp]
+    lib.b200gsr_compact_plan.argtypes = [i32, vp, vp, vp, vp, vp]
+    lib.b200gsr_gather_rows.argtypes = [i32, i32, vp, vp, vp, i32, vp]
+    lib.b200gsr_split_children.argtypes = [i32, i32, f, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.b200gsr_kth_smallest.argtypes = [i32, vp, u32, vp, vp, vp]
+    for fn in ("b200gsr_densify_stats", "b200gsr_densify_plan", "b200gsr_densify_map", "b200gsr_compact_plan",
+               "b200gsr_gather_rows", "b200gsr_split_children", "b200gsr_kth_smallest"):
+        getattr(lib, fn).restype = C.c_int
     lib.b200gsr_debug_counters.argtypes = [vp]
     lib.b200gsr_debug_counters.restype = C.c_int
     lib.b200gsr_profile_enable.argtypes = [i32]

@@ -428,6 +428,52 @@ int b200gsr_disparity_backward(int32_t B, int32_t N, const float* depth_alpha, c
                                                ds->num_sms, static_cast<cudaStream_t>(stream)), "disparity_backward");
 }
 
+#define GSR_ST(x) static_cast<cudaStream_t>(x)
+int b200gsr_densify_stats(int32_t P, const float* viewspace_grad, const int32_t* radii, float* accum, float* denom,
+                          float* max_radii2D, void* stream) {
+    if (P < 0 || (P > 0 && (!viewspace_grad || !radii || !accum || !denom))) return fail(B200GSR_ERR_BAD_ARG, "bad densify_stats arguments");
+    return check_cuda(gsr_densify_stats(P, viewspace_grad, radii, accum, denom, max_radii2D, GSR_ST(stream)), "densify_stats");
+}
+size_t b200gsr_densify_scratch_bytes(int32_t P) { return gsr_densify_scratch_bytes(P); }
+int b200gsr_densify_plan(int32_t P, const float* accum, const float* denom, const float* scaling, const float* opacity,
+                         float max_grad, float dense_extent, float min_opacity, float big_ws, float child_div,
+                         void* scratch, uint32_t* totals5, void* stream) {
+    if (P < 0 || !totals5 || (P > 0 && (!accum || !denom || !scaling || !opacity || !scratch)) || P > 0x0fffffff)
+        return fail(B200GSR_ERR_BAD_ARG, "bad densify_plan arguments");
+    return check_cuda(gsr_densify_plan(P, accum, denom, scaling, opacity, max_grad, dense_extent, min_opacity, big_ws,
+                                       child_div, scratch, totals5, GSR_ST(stream)), "densify_plan");
+}
+int b200gsr_densify_map(int32_t P, int32_t N, const void* scratch, const uint32_t* totals5, int32_t* src_map,
+                        int32_t* child_draw, void* stream) {
+    if (P < 0 || N < 1 || (P > 0 && (!scratch || !totals5 || !src_map || !child_draw)))
+        return fail(B200GSR_ERR_BAD_ARG, "bad densify_map arguments");
+    return check_cuda(gsr_densify_map(P, N, scratch, totals5, src_map, child_draw, GSR_ST(stream)), "densify_map");
+}
+int b200gsr_compact_plan(int32_t P, const uint8_t* keep, void* scratch, int32_t* src_map, uint32_t* count, void* stream) {
+    if (P < 0 || !count || (P > 0 && (!keep || !scratch || !src_map))) return fail(B200GSR_ERR_BAD_ARG, "bad compact_plan arguments");
+    return check_cuda(gsr_compact_plan(P, keep, scratch, src_map, count, GSR_ST(stream)), "compact_plan");
+}
+int b200gsr_gather_rows(int32_t n_out, int32_t row_floats, const int32_t* src_map, const float* in, float* out,
+                        int32_t zero_appended, void* stream) {
+    if (n_out < 0 || row_floats < 0 || (n_out > 0 && row_floats > 0 && (!src_map || !in || !out)))
+        return fail(B200GSR_ERR_BAD_ARG, "bad gather_rows arguments");
+    return check_cuda(gsr_gather_rows(n_out, row_floats, src_map, in, out, zero_appended, GSR_ST(stream)), "gather_rows");
+}
+int b200gsr_split_children(int32_t n_out, int32_t first_child, float child_div, const int32_t* src_map,
+                           const int32_t* child_draw, const float* xyz, const float* scaling, const float* rotation,
+                           const float* z, float* xyz_out, float* scaling_out, void* stream) {
+    if (n_out < 0 || first_child < 0 || (n_out > first_child && (!src_map || !child_draw || !xyz || !scaling || !rotation || !z || !xyz_out || !scaling_out)))
+        return fail(B200GSR_ERR_BAD_ARG, "bad split_children arguments");
+    return check_cuda(gsr_split_children(n_out, first_child, child_div, src_map, child_draw, xyz, scaling, rotation, z,
+                                         xyz_out, scaling_out, GSR_ST(stream)), "split_children");
+}
+int b200gsr_kth_smallest(int32_t n, const float* v, uint32_t k, void* scratch, float* out, void* stream) {
+    if (n < 0 || (n > 0 && (!v || !scratch || !out || k >= (uint32_t)n))) return fail(B200GSR_ERR_BAD_ARG, "bad kth_smallest arguments");
+    DeviceState* ds = device_state();
+    if (!ds) return fail(B200GSR_ERR_CUDA, "cannot query the current CUDA device");
+    return check_cuda(gsr_kth_smallest(n, v, k, scratch, out, ds->num_sms, GSR_ST(stream)), "kth_smallest");
+}
+
 int b200gsr_debug_counters(unsigned long long* device_counters) {
     g_stats = device_counters;
     return B200GSR_OK;

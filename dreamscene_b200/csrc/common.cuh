@@ -200,6 +200,23 @@ cudaError_t gsr_launch_disparity_fwd(int B, int N, const float* da, const float*
 cudaError_t gsr_launch_disparity_bwd(int B, int N, const float* da, const float* focal, const float* g_out,
                                      const float* g_alpha, void* stats, float* d_da, int num_sms, cudaStream_t s);
 
+// densification / pruning (densify.cu)
+cudaError_t gsr_densify_stats(int P, const float* vs_grad, const int32_t* radii, float* accum, float* denom,
+                              float* max_radii, cudaStream_t s);
+size_t gsr_densify_scratch_bytes(int P);
+cudaError_t gsr_densify_plan(int P, const float* accum, const float* denom, const float* scaling, const float* opacity,
+                             float max_grad, float dense_extent, float min_opacity, float big_ws, float child_div, void* scratch,
+                             uint32_t* totals5, cudaStream_t s);
+cudaError_t gsr_densify_map(int P, int N, const void* scratch, const uint32_t* totals5, int32_t* src_map,
+                            int32_t* child_draw, cudaStream_t s);
+cudaError_t gsr_compact_plan(int P, const uint8_t* keep, void* scratch, int32_t* src_map, uint32_t* count, cudaStream_t s);
+cudaError_t gsr_gather_rows(int n_out, int row_floats, const int32_t* src_map, const float* in, float* out,
+                            int zero_appended, cudaStream_t s);
+cudaError_t gsr_split_children(int n_out, int first_child, float child_div, const int32_t* src_map, const int32_t* child_draw,
+                               const float* xyz, const float* scaling, const float* rotation, const float* z,
+                               float* xyz_out, float* scaling_out, cudaStream_t s);
+cudaError_t gsr_kth_smallest(int n, const float* v, uint32_t k, void* scratch, float* out, int num_sms, cudaStream_t s);
+
 // simple_knn replacement (knn.cu)
 size_t gsr_knn_scratch_bytes(int P, int* max_cells_out);
 cudaError_t gsr_launch_knn(int P, const float* pts, float* out, uint8_t* scratch, cudaStream_t s);

@@ -111,9 +111,11 @@ class _Assemble(torch.autograd.Function):
 
 
 def assemble_scene(groups: Sequence, shs_aug: bool = True, scale_aug: bool = True, noise: str = "torch",
-                   seed: int | None = None, generator: torch.Generator | None = None):
+                   seed: int | None = None, generator: torch.Generator | None = None,
+                   z_shs: torch.Tensor | None = None, z_scales: torch.Tensor | None = None):
     """-> (means3D[P,3], opacities[P,1], scales[P,3], rotations[P,4], shs[P,M,3]) ready for
-    GaussianRasterizer, differentiable w.r.t. every group's raw leaves."""
+    GaussianRasterizer, differentiable w.r.t. every group's raw leaves.  z_shs [P,M,3] / z_scales [P,3]:
+    explicit standard-normal draws (noise="torch" only; drawn with torch.randn when omitted)."""
     if not 1 <= len(groups) <= _lib.MAX_GROUPS:
         raise ValueError(f"need 1..{_lib.MAX_GROUPS} groups")
     if noise not in ("torch", "fused"):
@@ -124,15 +126,19 @@ def assemble_scene(groups: Sequence, shs_aug: bool = True, scale_aug: bool = Tru
         raise RuntimeError("assemble_scene (b200gsr): parameters must be CUDA tensors; there is no CPU fallback")
     M = 1 + int(_get(groups[0], "_features_rest").shape[1])
     P = sum(int(_get(g, "_xyz").shape[0]) for g in groups)
-    z_shs = z_scales = None
     if noise == "torch":
         # the reference's order of draws: randn_like(shs) first, then randn_like(scales)
-        if shs_aug:
+        if shs_aug and z_shs is None:
             z_shs = torch.randn(P, M, 3, device=dev, generator=generator)
-        if scale_aug:
+        if scale_aug and z_scales is None:
             z_scales = torch.randn(P, 3, device=dev, generator=generator)
+        z_shs = _prep(z_shs) if shs_aug else None
+        z_scales = _prep(z_scales) if scale_aug else None
         seed = 0
-    elif seed is None:
-        seed = int(torch.randint(0, 2 ** 62, (1,), generator=generator if generator is not None and generator.device.type == "cpu" else None).item())
+    else:
+        z_shs = z_scales = None
+        if seed is None:
+            cpu_gen = generator if generator is not None and generator.device.type == "cpu" else None
+            seed = int(torch.randint(0, 2 ** 62, (1,), generator=cpu_gen).item())
     return _Assemble.apply(len(groups), M, NOISE_COEF if shs_aug else 0.0, NOISE_COEF if scale_aug else 0.0,
                            z_shs, z_scales, int(seed), *flat)

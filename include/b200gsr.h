@@ -234,6 +234,48 @@ int b200gsr_disparity_backward(int32_t B, int32_t N, const float* depth_alpha, c
                                float* d_depth_alpha, void* stream);
 
 /*
+ * densification / pruning primitives (/root/reference/gs_renderer.py:854-1087).
+ * All pointers are device pointers; `scratch` = b200gsr_densify_scratch_bytes(P) bytes.
+ *
+ * densify_stats  : add_densification_stats + the max_radii2D update for the view just rendered:
+ *                  where radii > 0: accum += |viewspace_grad[:, :2]|, denom += 1, max_radii2D = max(., radii)
+ * densify_plan   : the per-Gaussian decisions of densify_and_prune (clone / split / prune, in the
+ *                  reference's order and with its quirks) + prefix sums.  totals5 (device uint32[5]) =
+ *                  {kept originals, surviving clones, surviving split parents, split parents, sum};
+ *                  the new point count is totals5[0] + totals5[1] + N * totals5[2].
+ *                  dense_extent = percent_dense * extent; big_ws = 0.1 * extent or <= 0 (max_screen_size
+ *                  is None); child_div = 0.8 * N as float32.
+ * densify_map    : src_map[int32, new count]: bits 0..29 = source row, bits 30..31 = 0 original / 1 clone /
+ *                  2 split child, in the reference's output order [originals | clones | children, N blocks];
+ *                  child_draw[N * totals5[2]] = row of the reference's torch.normal(std=stds) draw each
+ *                  child consumes.
+ * compact_plan   : keep mask (uint8) -> src_map of the kept rows and their count (prune_points).
+ * gather_rows    : out[p, :] = in[src_map[p], :] for rows of `row_floats` floats; with zero_appended, rows
+ *                  whose source is a clone/child become zeros (Adam moments, statistics).
+ * split_children : xyz / log-scales of the children (rows >= first_child of the new arrays) from the
+ *                  parents' raw parameters and the caller's standard-normal draws z[N * split parents, 3].
+ * kth_smallest   : *out = k-th smallest (0-based) of v[n]: the percentile threshold of prune_gaussians
+ *                  without a sort.  scratch >= 1032 bytes.
+ */
+int b200gsr_densify_stats(int32_t P, const float* viewspace_grad, const int32_t* radii, float* accum,
+                          float* denom, float* max_radii2D, void* stream);
+size_t b200gsr_densify_scratch_bytes(int32_t P);
+int b200gsr_densify_plan(int32_t P, const float* accum, const float* denom, const float* scaling,
+                         const float* opacity, float max_grad, float dense_extent, float min_opacity,
+                         float big_ws, float child_div, void* scratch, uint32_t* totals5, void* stream);
+int b200gsr_densify_map(int32_t P, int32_t N, const void* scratch, const uint32_t* totals5,
+                        int32_t* src_map, int32_t* child_draw, void* stream);
+int b200gsr_compact_plan(int32_t P, const uint8_t* keep, void* scratch, int32_t* src_map, uint32_t* count,
+                         void* stream);
+int b200gsr_gather_rows(int32_t n_out, int32_t row_floats, const int32_t* src_map, const float* in, float* out,
+                        int32_t zero_appended, void* stream);
+int b200gsr_split_children(int32_t n_out, int32_t first_child, float child_div, const int32_t* src_map,
+                           const int32_t* child_draw, const float* xyz, const float* scaling,
+                           const float* rotation, const float* z, float* xyz_out, float* scaling_out,
+                           void* stream);
+int b200gsr_kth_smallest(int32_t n, const float* v, uint32_t k, void* scratch, float* out, void* stream);
+
+/*
  * replaces simple_knn._C.distCUDA2 (un-vendored; /root/reference/gs_renderer.py:9,590-593):
  * out[i] = mean of the squared distances from points[i] to its 3 nearest OTHER points (points f32[P,3]).
  * `scratch` = b200gsr_dist2_scratch_bytes(P) bytes of device memory.

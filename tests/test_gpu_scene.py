@@ -25,10 +25,14 @@ def test_assemble_matches_reference_expressions_forward_and_backward(M, sizes):
     groups = _groups(sizes, M)
     P = sum(sizes)
     gen = torch.Generator(device="cuda").manual_seed(7)
-    got = assemble_scene(groups, noise="torch", generator=gen)
+    drawn = assemble_scene(groups, noise="torch", generator=gen)
     gen = torch.Generator(device="cuda").manual_seed(7)          # the reference's draws: shs first, then scales
     z_shs = torch.randn(P, M, 3, device="cuda", generator=gen)
     z_scales = torch.randn(P, 3, device="cuda", generator=gen)
+    same_stream = reference_assemble(groups, z_shs, z_scales)
+    assert torch.equal(drawn[4], same_stream[4]) and torch.equal(drawn[2], same_stream[2])   # same RNG stream as the reference
+    z_scales[::5] = -10.0                                        # 1 + 0.1118 z < 0: exercises the clamp at exactly 0
+    got = assemble_scene(groups, noise="torch", z_shs=z_shs, z_scales=z_scales)
     ref_groups = [{k: v.detach().clone().requires_grad_(True) for k, v in g.items()} for g in groups]
     want = reference_assemble(ref_groups, z_shs, z_scales)
     names = ("means3D", "opacity", "scales", "rotations", "shs")
