@@ -22,6 +22,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dreamscene_b200 import GaussianRasterizationSettings, GaussianRasterizer  # noqa: E402
+from dreamscene_b200.multiview import rasterize_views  # noqa: E402
 from dreamscene_b200.postprocess import disparity_from_depth_alpha  # noqa: E402
 from dreamscene_b200.scene import assemble_scene  # noqa: E402
 from harness import cameras  # noqa: E402
@@ -120,13 +121,37 @@ def render(groups, cam, dev, bg, aug=True, glue="torch"):
     return dict(image=image, depth=disp, alpha=alpha, radii=radii, viewspace=screenspace, ev=(t0, t1))
 
 
+def render_views(groups, cams, dev, bg, aug=True):
+    """All views of the step in one rasterizer pass (dreamscene_b200.multiview): per-view augmented shs / scales
+    (in-kernel Philox noise), shared positions / opacities / rotations, batched fused disparity."""
+    named = [{"_xyz": g["xyz"], "_opacity": g["opacity"], "_scaling": g["scaling"], "_rotation": g["rotation"],
+              "_features_dc": g["f_dc"], "_features_rest": g["f_rest"]} for g in groups]
+    per_view = [assemble_scene(named, shs_aug=aug, scale_aug=aug, noise="fused") for _ in cams]
+    xyz, opacity, _, rots, _ = per_view[0]
+    S = [GaussianRasterizationSettings(
+        image_height=c.image_height, image_width=c.image_width, tanfovx=c.tanfovx, tanfovy=c.tanfovy, bg=bg,
+        scale_modifier=1.0, viewmatrix=c.world_view_transform, projmatrix=c.full_proj_transform, sh_degree=1,
+        campos=c.camera_center, prefiltered=False, score_flag=False) for c in cams]
+    screens = [torch.zeros_like(xyz, requires_grad=True) for _ in cams]
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    outs = rasterize_views(S, xyz, opacity, shs=[p[4] for p in per_view], scales=[p[2] for p in per_view], rotations=rots,
+                           means2D=screens)
+    t1.record()
+    da = torch.stack([o[2] for o in outs])                                  # [B,2,H,W]
+    focals = [1 / (2 * math.tan(c.FoVx / 2)) for c in cams]
+    disp, alpha = disparity_from_depth_alpha(da, focals)
+    return [dict(image=o[0], depth=disp[v], alpha=alpha[v], radii=o[1], viewspace=screens[v], ev=(t0, t1) if v == 0 else None)
+            for v, o in enumerate(outs)]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--views", type=int, default=4)
     ap.add_argument("--size", type=int, default=512)
-    ap.add_argument("--glue", default="torch", choices=["torch", "fused", "fused_rng"])
+    ap.add_argument("--glue", default="torch", choices=["torch", "fused", "fused_rng", "views"])
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
@@ -141,14 +166,15 @@ def main():
         for p in params:
             p.grad = None
         torch.cuda.synchronize(); t0 = time.perf_counter()
-        outs = [render(groups, scene_camera(it * a.views + k, a.size, dev), dev, bg, glue=a.glue) for k in range(a.views)]
+        cams = [scene_camera(it * a.views + k, a.size, dev) for k in range(a.views)]
+        outs = render_views(groups, cams, dev, bg) if a.glue == "views" else [render(groups, c, dev, bg, glue=a.glue) for c in cams]
         images = torch.stack([o["image"] for o in outs]); depths = torch.stack([o["depth"] for o in outs])
         loss = ((images - target) ** 2).mean() * 100 + depths.mean() * 0.1      # SDS -> L2 stub (+ depth path)
         loss.backward()
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
         if it >= a.warmup:
             times.append(dt)
-            ras_fwd.append(sum(o["ev"][0].elapsed_time(o["ev"][1]) for o in outs))
+            ras_fwd.append(sum(o["ev"][0].elapsed_time(o["ev"][1]) for o in outs if o["ev"] is not None))
             vis.append(float(np.mean([(o["radii"] > 0).float().mean().item() for o in outs])))
             pairs.append(R.last_pair_count(dev))
     finite = all(torch.isfinite(p.grad).all().item() for p in params)

@@ -15,7 +15,8 @@ EXPORTS = ["b200gsr_version", "b200gsr_last_error", "b200gsr_saved_layout_query"
            "b200gsr_assemble_forward", "b200gsr_assemble_backward", "b200gsr_disparity_forward",
            "b200gsr_disparity_backward", "b200gsr_densify_stats", "b200gsr_densify_scratch_bytes",
            "b200gsr_densify_plan", "b200gsr_densify_map", "b200gsr_compact_plan", "b200gsr_gather_rows",
-           "b200gsr_split_children", "b200gsr_kth_smallest"]
+           "b200gsr_split_children", "b200gsr_kth_smallest", "b200gsr_views_geometry", "b200gsr_forward_views",
+           "b200gsr_backward_views"]
 
 
 class Params(C.Structure):
@@ -36,6 +37,16 @@ class GroupGrad(C.Structure):       # == b200gsr_group_grad
 
 
 MAX_GROUPS = 24
+MAX_VIEWS = 16
+
+
+class ViewInputs(C.Structure):      # == b200gsr_view_inputs
+    _fields_ = [(n, C.c_void_p) for n in ("means3D", "shs", "colors_precomp", "opacities", "scales", "rotations", "cov3D_precomp")]
+
+
+class ViewGrads(C.Structure):       # == b200gsr_view_grads
+    _fields_ = [(n, C.c_void_p) for n in ("d_means3D", "d_means2D", "d_shs", "d_colors", "d_opacities", "d_scales",
+                                          "d_rotations", "d_cov3D")] + [("accumulate", C.c_uint32)]
 
 
 class SavedLayout(C.Structure):
@@ -107,6 +118,13 @@ def load():
     lib.b200gsr_kth_smallest.argtypes = [i32, vp, u32, vp, vp, vp]
     for fn in ("b200gsr_densify_stats", "b200gsr_densify_plan", "b200gsr_densify_map", "b200gsr_compact_plan",
                "b200gsr_gather_rows", "b200gsr_split_children", "b200gsr_kth_smallest"):
+        getattr(lib, fn).restype = C.c_int
+    lib.b200gsr_views_geometry.argtypes = [i32, i32, i32, C.POINTER(i32)]
+    lib.b200gsr_forward_views.argtypes = [i32, C.POINTER(Params), C.POINTER(ViewInputs), vp, vp, vp, vp, vp, sz, vp, sz,
+                                          u64, u32, vp, u32, vp]
+    lib.b200gsr_backward_views.argtypes = [i32, C.POINTER(Params), C.POINTER(ViewInputs), vp, vp, vp, vp, vp, sz, u64,
+                                           C.POINTER(ViewGrads), vp]
+    for fn in ("b200gsr_views_geometry", "b200gsr_forward_views", "b200gsr_backward_views"):
         getattr(lib, fn).restype = C.c_int
     lib.b200gsr_debug_counters.argtypes = [vp]
     lib.b200gsr_debug_counters.restype = C.c_int

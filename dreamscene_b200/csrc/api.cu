@@ -192,6 +192,7 @@ int b200gsr_forward(const b200gsr_params* prm, const float* means3D, const float
     a.max_pairs = (uint32_t)max_pairs;
     a.host_notify = host_notify; a.notify_seq = notify_seq;
     a.flags = flags; a.num_sms = ds->num_sms; a.stats = g_stats;
+    a.view = 0; a.num_views = 1; a.P_view = prm->P; a.gy_view = gsr_grid(prm->image_height, prm->image_width).gy;
     a.stream = static_cast<cudaStream_t>(stream);
 
     // The queue counters and the per-tile pair counters (contiguous at the start of scratch) must be
@@ -277,6 +278,8 @@ int b200gsr_backward_ex(const b200gsr_params* prm, const float* means3D, const f
     a.d_opac = d_opacities; a.d_scales = d_scales; a.d_rots = d_rotations; a.d_cov3d = d_cov3D;
     a.num_sms = ds->num_sms; a.stats = g_stats;
     a.g_begin = g_begin; a.g_end = g_end; a.dsh_coefs = dsh_coefs;
+    a.view = 0; a.num_views = 1; a.P_view = prm->P; a.gy_view = gsr_grid(prm->image_height, prm->image_width).gy;
+    a.accumulate = 0;
     a.stream = static_cast<cudaStream_t>(stream);
 
     // no memsets: the work-queue counters and the gradient accumulators live in `saved`, zeroed by
@@ -315,6 +318,139 @@ int b200gsr_backward(const b200gsr_params* prm, const float* means3D, const floa
                                out_depth_alpha, dL_dcolor, dL_ddepth_alpha, saved, saved_bytes, scratch, scratch_bytes,
                                max_pairs, d_means3D, d_means2D, d_shs, d_colors, d_opacities, d_scales, d_rotations,
                                d_cov3D, B200GSR_BWD_COMPOSITE | B200GSR_BWD_PROJECT, 0, prm ? prm->P : 0, 0, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-view entry points: B views of the same image size in ONE binning / sort /
+// composite pass.  The views are stacked vertically into an image of B * gy tile rows and view v's
+// Gaussians become the virtual Gaussians [v*P, (v+1)*P): only the two per-Gaussian stages run per view
+// (each with its own camera and, if the caller wishes, its own parameter tensors).
+// ---------------------------------------------------------------------------------------------
+static int check_views(int32_t B, const b200gsr_params* prm, const b200gsr_view_inputs* in) {
+    if (B < 1 || B > B200GSR_MAX_VIEWS) return fail(B200GSR_ERR_UNSUPPORTED, "number of views %d not in 1..%d", B, B200GSR_MAX_VIEWS);
+    if (!prm || !in) return fail(B200GSR_ERR_BAD_ARG, "null view array");
+    for (int v = 0; v < B; ++v) {
+        int rc = validate_inputs(&prm[v], in[v].means3D, in[v].shs, in[v].colors_precomp, in[v].opacities, in[v].scales,
+                                 in[v].rotations, in[v].cov3D_precomp);
+        if (rc) return rc;
+        if (prm[v].P != prm[0].P || prm[v].M != prm[0].M || prm[v].image_height != prm[0].image_height ||
+            prm[v].image_width != prm[0].image_width || prm[v].score_flag != prm[0].score_flag)
+            return fail(B200GSR_ERR_BAD_ARG, "view %d: P, M, image size and score_flag must equal view 0's", v);
+        if (prm[v].bg != prm[0].bg + 3 * v)
+            return fail(B200GSR_ERR_BAD_ARG, "view %d: backgrounds must be one contiguous device array [B,3] (prm[v].bg = prm[0].bg + 3 v)", v);
+        if ((in[v].shs != nullptr) != (in[0].shs != nullptr) || (in[v].cov3D_precomp != nullptr) != (in[0].cov3D_precomp != nullptr))
+            return fail(B200GSR_ERR_BAD_ARG, "view %d: all views must use the same input kinds", v);
+    }
+    if ((long long)B * prm[0].P > 0x3fffffffLL) return fail(B200GSR_ERR_UNSUPPORTED, "B * P too large");
+    return B200GSR_OK;
+}
+
+int b200gsr_views_geometry(int32_t B, int32_t H, int32_t W, int32_t* stacked_height) {
+    if (B < 1 || H < 0 || W < 0 || !stacked_height) return fail(B200GSR_ERR_BAD_ARG, "bad views_geometry arguments");
+    *stacked_height = B * gsr_grid(H, W).gy * GSR_TILE;
+    return B200GSR_OK;
+}
+
+int b200gsr_forward_views(int32_t B, const b200gsr_params* prm, const b200gsr_view_inputs* in, float* out_color,
+                          float* out_depth_alpha, int32_t* radii, float* score, void* scratch, size_t scratch_bytes,
+                          void* saved, size_t saved_bytes, uint64_t max_pairs, uint32_t flags, uint32_t* host_notify,
+                          uint32_t notify_seq, void* stream) {
+    int rc = check_views(B, prm, in);
+    if (rc) return rc;
+    const int P = prm[0].P, H = prm[0].image_height, W = prm[0].image_width;
+    if (!out_color || !out_depth_alpha || (P > 0 && !radii) || !scratch || !saved)
+        return fail(B200GSR_ERR_BAD_ARG, "null output/workspace pointer");
+    if (prm[0].score_flag && P > 0 && !score) return fail(B200GSR_ERR_BAD_ARG, "score_flag set but score buffer is null");
+    DeviceState* ds = device_state();
+    if (!ds) return fail(B200GSR_ERR_CUDA, "cannot query the current CUDA device");
+    const GsrTileGrid g1 = gsr_grid(H, W);
+    const int Hs = B * g1.gy * GSR_TILE;
+    GsrFwdArgs a;
+    const int with_bwd = (flags & B200GSR_FWD_NO_BACKWARD) ? 0 : 1;
+    if ((rc = b200gsr_scratch_layout_query(B * P, Hs, W, max_pairs, &a.sl))) return rc;
+    if ((rc = b200gsr_saved_layout_query(B * P, Hs, W, max_pairs, with_bwd, &a.vl))) return rc;
+    if (scratch_bytes < a.sl.total || saved_bytes < a.vl.total)
+        return fail(B200GSR_ERR_WORKSPACE, "workspace too small: scratch %zu < %zu or saved %zu < %zu",
+                    scratch_bytes, a.sl.total, saved_bytes, a.vl.total);
+    a.out_color = out_color; a.out_depth_alpha = out_depth_alpha; a.score = score; a.radii = radii;
+    a.scratch = static_cast<uint8_t*>(scratch); a.saved = static_cast<uint8_t*>(saved);
+    a.max_pairs = (uint32_t)max_pairs;
+    a.host_notify = host_notify; a.notify_seq = notify_seq;
+    a.flags = flags; a.num_sms = ds->num_sms; a.stats = g_stats;
+    a.num_views = B; a.P_view = P; a.gy_view = g1.gy;
+    a.stream = static_cast<cudaStream_t>(stream);
+    const int ntiles = g1.gx * g1.gy * B;
+    if (!gsr_use_multisplit(ntiles) || P == 0) {
+        const size_t nbytes = gsr_use_multisplit(ntiles) ? a.sl.tile_count + (size_t)ntiles * sizeof(uint32_t) : a.sl.tile_cursor;
+        if ((rc = check_cuda(cudaMemsetAsync(a.scratch, 0, nbytes, a.stream), "memset"))) return rc;
+    }
+    GSR_RANGE_PUSH("b200gsr.views.project_sh");
+    for (int v = 0; v < B && !rc; ++v) {
+        a.prm = prm[v]; a.view = v;
+        a.means3D = in[v].means3D; a.shs = in[v].shs; a.colors = in[v].colors_precomp; a.opac = in[v].opacities;
+        a.scales = in[v].scales; a.rots = in[v].rotations; a.cov3d = in[v].cov3D_precomp;
+        rc = check_cuda(gsr_launch_project(a), "project_sh");
+    }
+    GSR_RANGE_POP();
+    if (rc) return rc;
+    a.prm = prm[0]; a.view = 0;     // per-view constants are not used past this point (bg is indexed by tile row)
+    GSR_RANGE_PUSH("b200gsr.views.binning+sort+composite");
+    rc = check_cuda(gsr_launch_count(a), "tile_count");
+    if (!rc) rc = check_cuda(gsr_launch_scan(a), "scan_order");
+    if (!rc) rc = check_cuda(gsr_launch_scatter(a), "scatter");
+    if (!rc) rc = check_cuda(gsr_launch_sort(a, ds->stream, ds->fork, ds->join), "tile_sort");
+    if (!rc) rc = check_cuda(gsr_launch_composite_fwd(a), "composite_fwd");
+    GSR_RANGE_POP();
+    return rc;
+}
+
+int b200gsr_backward_views(int32_t B, const b200gsr_params* prm, const b200gsr_view_inputs* in, const int32_t* radii,
+                           const float* out_depth_alpha, const float* dL_dcolor, const float* dL_ddepth_alpha,
+                           void* saved, size_t saved_bytes, uint64_t max_pairs, const b200gsr_view_grads* out,
+                           void* stream) {
+    int rc = check_views(B, prm, in);
+    if (rc) return rc;
+    const int P = prm[0].P, H = prm[0].image_height, W = prm[0].image_width;
+    if (P == 0) return B200GSR_OK;
+    if (!radii || !out_depth_alpha || !dL_dcolor || !dL_ddepth_alpha || !saved || !out)
+        return fail(B200GSR_ERR_BAD_ARG, "null saved-state/gradient pointer");
+    DeviceState* ds = device_state();
+    if (!ds) return fail(B200GSR_ERR_CUDA, "cannot query the current CUDA device");
+    const GsrTileGrid g1 = gsr_grid(H, W);
+    const int Hs = B * g1.gy * GSR_TILE;
+    GsrBwdArgs a;
+    a.sl = b200gsr_scratch_layout{};
+    if ((rc = b200gsr_saved_layout_query(B * P, Hs, W, max_pairs, 1, &a.vl))) return rc;
+    if (saved_bytes < a.vl.total) return fail(B200GSR_ERR_WORKSPACE, "saved buffer too small for backward: %zu < %zu", saved_bytes, a.vl.total);
+    a.radii = radii; a.out_depth_alpha = out_depth_alpha; a.dL_dcolor = dL_dcolor; a.dL_ddepth_alpha = dL_ddepth_alpha;
+    a.saved = static_cast<uint8_t*>(saved); a.scratch = nullptr; a.max_pairs = (uint32_t)max_pairs;
+    a.num_sms = ds->num_sms; a.stats = g_stats;
+    a.num_views = B; a.P_view = P; a.gy_view = g1.gy; a.dsh_coefs = 0; a.g_begin = 0; a.g_end = P;
+    a.stream = static_cast<cudaStream_t>(stream);
+    a.prm = prm[0]; a.view = 0; a.accumulate = 0;
+    a.means3D = in[0].means3D; a.shs = in[0].shs; a.colors = in[0].colors_precomp; a.opac = in[0].opacities;
+    a.scales = in[0].scales; a.rots = in[0].rotations; a.cov3d = in[0].cov3D_precomp;
+    GSR_RANGE_PUSH("b200gsr.views.composite_bwd");
+    rc = check_cuda(gsr_launch_composite_bwd(a), "composite_bwd");
+    GSR_RANGE_POP();
+    if (rc) return rc;
+    GSR_RANGE_PUSH("b200gsr.views.project_bwd");
+    for (int v = 0; v < B && !rc; ++v) {
+        const b200gsr_view_grads& o = out[v];
+        if (!o.d_means3D || !o.d_means2D || !o.d_opacities || (in[v].shs && !o.d_shs) || (in[v].colors_precomp && !o.d_colors) ||
+            (in[v].cov3D_precomp && !o.d_cov3D) || (!in[v].cov3D_precomp && (!o.d_scales || !o.d_rotations))) {
+            rc = fail(B200GSR_ERR_BAD_ARG, "view %d: null gradient output pointer", v);
+            break;
+        }
+        a.prm = prm[v]; a.view = v; a.accumulate = (int)o.accumulate;
+        a.means3D = in[v].means3D; a.shs = in[v].shs; a.colors = in[v].colors_precomp; a.opac = in[v].opacities;
+        a.scales = in[v].scales; a.rots = in[v].rotations; a.cov3d = in[v].cov3D_precomp;
+        a.d_means3D = o.d_means3D; a.d_means2D = o.d_means2D; a.d_shs = o.d_shs; a.d_colors = o.d_colors;
+        a.d_opac = o.d_opacities; a.d_scales = o.d_scales; a.d_rots = o.d_rotations; a.d_cov3d = o.d_cov3D;
+        rc = check_cuda(gsr_launch_project_bwd(a), "project_bwd");
+    }
+    GSR_RANGE_POP();
+    return rc;
 }
 
 int b200gsr_profile_enable(int32_t max_calls) {

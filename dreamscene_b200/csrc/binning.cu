@@ -676,6 +676,7 @@ struct BinPtrs {
 BinPtrs bin_ptrs(const GsrFwdArgs& a) {
     BinPtrs b;
     b.grid = gsr_grid(a.prm.image_height, a.prm.image_width);
+    if (a.num_views > 1) { b.grid.gy = a.num_views * a.gy_view; b.grid.ntiles = b.grid.gx * b.grid.gy; }
     b.header = reinterpret_cast<uint32_t*>(a.saved + a.vl.header);
     b.tile_start = reinterpret_cast<uint32_t*>(a.saved + a.vl.tile_start);
     b.work_order = reinterpret_cast<uint32_t*>(a.saved + a.vl.work_order);
@@ -707,7 +708,7 @@ cudaError_t gsr_launch_scan(const GsrFwdArgs& a) {
 }
 
 static cudaError_t launch_multisplit(const GsrFwdArgs& a, const BinPtrs& b, bool scatter) {
-    const int P = a.prm.P;
+    const int P = a.num_views * a.P_view;     // virtual Gaussians (view-major)
     if (P == 0) return cudaSuccess;
     const int per = 1024 * GSR_MS_ITEMS;
     const int smem = 2 * b.grid.ntiles * (int)sizeof(uint32_t);
@@ -737,8 +738,9 @@ cudaError_t gsr_launch_count(const GsrFwdArgs& a) {
 cudaError_t gsr_launch_scatter(const GsrFwdArgs& a) {
     const BinPtrs b = bin_ptrs(a);
     if (gsr_use_multisplit(b.grid.ntiles)) return launch_multisplit(a, b, true);
-    if (a.prm.P > 0)
-        scatter_kernel<<<(a.prm.P + 255) / 256, 256, 0, a.stream>>>(a.prm.P, b.grid.gx, b.grid.ntiles,
+    const int PV = a.num_views * a.P_view;
+    if (PV > 0)
+        scatter_kernel<<<(PV + 255) / 256, 256, 0, a.stream>>>(PV, b.grid.gx, b.grid.ntiles,
                                                                      a.max_pairs, b.rectdepth, b.tile_cursor,
                                                                      b.keys);
     return cudaGetLastError();

@@ -140,6 +140,10 @@ struct GsrFwdArgs {
     uint32_t* host_notify;
     uint32_t notify_seq;
     uint32_t flags;        // B200GSR_FWD_*
+    // multi-view (b200gsr_forward_views): the views are stacked vertically into one image of
+    // num_views * gy_view tile rows; view v's Gaussians are the virtual Gaussians [v*P_view, (v+1)*P_view).
+    // Single-view calls: view = 0, num_views = 1, P_view = prm.P, gy_view = tile rows of the image.
+    int view, num_views, P_view, gy_view;
     int num_sms;           // of the current device (cached per device in api.cu)
     unsigned long long* stats;
     cudaStream_t stream;
@@ -156,6 +160,8 @@ struct GsrBwdArgs {
     b200gsr_saved_layout vl;
     uint32_t max_pairs;
     float *d_means3D, *d_means2D, *d_shs, *d_colors, *d_opac, *d_scales, *d_rots, *d_cov3d;
+    int view, num_views, P_view, gy_view;   // see GsrFwdArgs
+    int accumulate;        // project_bwd adds into the gradient outputs instead of overwriting (views sharing a parameter)
     int g_begin, g_end;    // Gaussian range of the project_bwd stage (chunked launches)
     int dsh_coefs;         // coefficients per row of d_shs (0 = M, the reference layout)
     int num_sms;

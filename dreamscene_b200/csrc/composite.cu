@@ -123,7 +123,7 @@ struct __align__(128) SmemCta {
 
 template <bool SCORE, int PPL, bool STATS>
 __global__ void __launch_bounds__(256 / PPL)
-composite_fwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restrict__ header,
+composite_fwd_kernel(int H, int W, int gx, int gy_view, int Hs, int ntiles, const uint32_t* __restrict__ header,
                      const uint32_t* __restrict__ work_order,
                      const uint32_t* __restrict__ tile_start,
                      const unsigned long long* __restrict__ keys, const GsrRec* __restrict__ geom,
@@ -138,7 +138,6 @@ composite_fwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restric
     SmemCta& sm = *reinterpret_cast<SmemCta*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t max_pairs = header[GSR_H_MAX_PAIRS];
-    const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
 
     for (;;) {
         // one shared counter over ALL tiles (empty ones included, they come last): measured faster
@@ -155,7 +154,13 @@ composite_fwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restric
         const int n = (int)(end - beg);
         const int nchunks = (n + kChunk - 1) / kChunk;
         const unsigned long long* tk = keys + beg;
-        const int tyi = tile / gx, txi = tile - tyi * gx;
+        const int tys = tile / gx, txi = tile - tys * gx;
+        // multi-view: tile row tys of the stacked image = row tyi of view `view`; everything is evaluated in
+        // view-local pixel coordinates (bit-identical to a single-view render), only addressing is stacked
+        const int view = tys / gy_view, tyi = tys - view * gy_view;
+        const int row0 = view * gy_view * GSR_TILE;
+        const float* bgv = bg + 3 * view;
+        const float bg0 = __ldg(bgv), bg1 = __ldg(bgv + 1), bg2 = __ldg(bgv + 2);
         const int X0i = txi * GSR_TILE + (wid & 1) * 8, Y0i = tyi * GSR_TILE + (wid >> 1) * (4 * PPL);
         const int Xi = X0i + (lane & 7), Yi = Y0i + (lane >> 3);
         const float X0 = (float)X0i, Y0 = (float)Y0i, X = (float)Xi;
@@ -252,11 +257,11 @@ composite_fwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restric
         }
         cp_async_wait<0>();   // never leave copies in flight across tiles (early-out case)
 
-        const size_t plane = (size_t)H * W;
+        const size_t plane = (size_t)Hs * W;
 #pragma unroll
         for (int q = 0; q < PPL; ++q) {
             if (inside[q]) {
-                const size_t pix = (size_t)(Yi + 4 * q) * W + Xi;
+                const size_t pix = (size_t)(row0 + Yi + 4 * q) * W + Xi;
                 out_color[pix] = fmaf(T[q], bg0, Cr[q]);
                 out_color[plane + pix] = fmaf(T[q], bg1, Cg[q]);
                 out_color[2 * plane + pix] = fmaf(T[q], bg2, Cb[q]);
@@ -510,7 +515,7 @@ __device__ __forceinline__ int bwd_value_index(int lane) {
 
 template <int kSlots, int kMinCtas>
 __global__ void __launch_bounds__(kWarps * 32, kMinCtas)
-composite_bwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restrict__ header,
+composite_bwd_kernel(int H, int W, int gx, int gy_view, int Hs, int ntiles, const uint32_t* __restrict__ header,
                      const uint32_t* __restrict__ work_order,
                      const uint32_t* __restrict__ tile_start,
                      const unsigned long long* __restrict__ keys, const GsrRec* __restrict__ geom,
@@ -524,10 +529,9 @@ composite_bwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restric
     GsrRec (*ring)[32] = sm.rec[wid];
     const uint32_t max_pairs = header[GSR_H_MAX_PAIRS];
     const uint32_t nonempty = header[GSR_H_NUM_NONEMPTY];
-    const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
     const int vidx = bwd_value_index(lane);
     const bool commit_lane = (vidx >= 0) && !(lane & 1);
-    const size_t plane = (size_t)H * W;
+    const size_t plane = (size_t)Hs * W;
 
     uint32_t qsel = (blockIdx.x * kWarps + wid) % GSR_NQUEUE, qtried = 0;
     for (;;) {
@@ -539,14 +543,18 @@ composite_bwd_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restric
         if (end > max_pairs) end = max_pairs;
         if (beg > end) beg = end;
         const unsigned long long* tk = keys + beg;
-        const int tyi = tile / gx, txi = tile - tyi * gx;
+        const int tys = tile / gx, txi = tile - tys * gx;
+        const int view = tys / gy_view, tyi = tys - view * gy_view;      // view-local evaluation, stacked addressing
+        const int row0 = view * gy_view * GSR_TILE;
+        const float* bgv = bg + 3 * view;
+        const float bg0 = __ldg(bgv), bg1 = __ldg(bgv + 1), bg2 = __ldg(bgv + 2);
         const int X0i = txi * GSR_TILE + (blk & 1) * 8, Y0i = tyi * GSR_TILE + (blk >> 1) * 4;
         const int Xi = X0i + (lane & 7), Yi = Y0i + (lane >> 3);
         const float X0 = (float)X0i, Y0 = (float)Y0i, X = (float)Xi, Y = (float)Yi;
         uint32_t last = 0;
         float Tfinal = 1.f, dC0 = 0.f, dC1 = 0.f, dC2 = 0.f, dD = 0.f, dT = 0.f;
         if (Xi < W && Yi < H) {
-            const size_t pix = (size_t)Yi * W + Xi;
+            const size_t pix = (size_t)(row0 + Yi) * W + Xi;
             last = n_contrib[pix];
             Tfinal = out_depth_alpha[plane + pix];
             dC0 = dL_dcolor[pix]; dC1 = dL_dcolor[plane + pix]; dC2 = dL_dcolor[2 * plane + pix];
@@ -694,7 +702,7 @@ __device__ __forceinline__ void halve2(float (&v)[10], bool hi) {
 
 template <int kSlots, int kMinCtas, int KFAST, bool STATS>
 __global__ void __launch_bounds__(kWarps * 32, kMinCtas)
-composite_bwd2_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restrict__ header,
+composite_bwd2_kernel(int H, int W, int gx, int gy_view, int Hs, int ntiles, const uint32_t* __restrict__ header,
                       const uint32_t* __restrict__ work_order,
                       const uint32_t* __restrict__ tile_start,
                       const unsigned long long* __restrict__ keys, const GsrRec* __restrict__ geom,
@@ -709,10 +717,9 @@ composite_bwd2_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restri
     GsrRec (*ring)[32] = sm.rec[wid];
     const uint32_t max_pairs = header[GSR_H_MAX_PAIRS];
     const uint32_t nonempty = header[GSR_H_NUM_NONEMPTY];
-    const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
     const int vidx = bwd_value_index(lane);
     const bool commit_lane = (vidx >= 0) && !(lane & 1);
-    const size_t plane = (size_t)H * W;
+    const size_t plane = (size_t)Hs * W;
     unsigned long long st_eval = 0, st_contrib = 0, st_lanes = 0;
     unsigned long long st_hist[6] = {0, 0, 0, 0, 0, 0};
 
@@ -726,7 +733,11 @@ composite_bwd2_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restri
         if (end > max_pairs) end = max_pairs;
         if (beg > end) beg = end;
         const unsigned long long* tk = keys + beg;
-        const int tyi = tile / gx, txi = tile - tyi * gx;
+        const int tys = tile / gx, txi = tile - tys * gx;
+        const int view = tys / gy_view, tyi = tys - view * gy_view;      // view-local evaluation, stacked addressing
+        const int row0 = view * gy_view * GSR_TILE;
+        const float* bgv = bg + 3 * view;
+        const float bg0 = __ldg(bgv), bg1 = __ldg(bgv + 1), bg2 = __ldg(bgv + 2);
         const int X0i = txi * GSR_TILE + (blk & 1) * 8, Y0i = tyi * GSR_TILE + (blk >> 1) * 4;
         const int Xi = X0i + (lane & 7), Yi = Y0i + (lane >> 3);
         const float X0 = (float)X0i, Y0 = (float)Y0i;
@@ -735,7 +746,7 @@ composite_bwd2_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restri
         float Tfinal = 1.f, dT = 0.f;
         float2 dC01 = make_float2(0.f, 0.f), dC2D = make_float2(0.f, 0.f);
         if (Xi < W && Yi < H) {
-            const size_t pix = (size_t)Yi * W + Xi;
+            const size_t pix = (size_t)(row0 + Yi) * W + Xi;
             last = n_contrib[pix];
             Tfinal = out_depth_alpha[plane + pix];
             dC01.x = dL_dcolor[pix]; dC01.y = dL_dcolor[plane + pix]; dC2D.x = dL_dcolor[2 * plane + pix];
@@ -880,14 +891,20 @@ composite_bwd2_kernel(int H, int W, int gx, int ntiles, const uint32_t* __restri
 
 struct CompPtrs {
     GsrTileGrid grid;
+    int H;                 // height of the (stacked) image the kernels render
     const uint32_t *header, *tile_start, *work_order;
     const unsigned long long* keys;
     const GsrRec* geom;
     uint32_t* n_contrib;
 };
-static CompPtrs comp_ptrs(const uint8_t* saved, const b200gsr_saved_layout& vl, int H, int W) {
+static CompPtrs comp_ptrs(const uint8_t* saved, const b200gsr_saved_layout& vl, int H, int W, int num_views, int gy_view) {
     CompPtrs c;
     c.grid = gsr_grid(H, W);
+    c.H = H;
+    if (num_views > 1) {   // views stacked vertically, each padded to whole tile rows
+        c.grid.gy = num_views * gy_view; c.grid.ntiles = c.grid.gx * c.grid.gy;
+        c.H = c.grid.gy * GSR_TILE;
+    }
     c.header = reinterpret_cast<const uint32_t*>(saved + vl.header);
     c.tile_start = reinterpret_cast<const uint32_t*>(saved + vl.tile_start);
     c.work_order = reinterpret_cast<const uint32_t*>(saved + vl.work_order);
@@ -904,7 +921,7 @@ static cudaError_t launch_fwd(const GsrFwdArgs& a, int nblocks, const CompPtrs& 
     cudaError_t e = gsr_smem_once(composite_fwd_kernel<SCORE, 1, STATS>, smem, attr_done);
     if (e != cudaSuccess) return e;
     composite_fwd_kernel<SCORE, 1, STATS><<<nblocks, 256, smem, a.stream>>>(
-        a.prm.image_height, a.prm.image_width, c.grid.gx, c.grid.ntiles, c.header, c.work_order, c.tile_start,
+        a.prm.image_height, a.prm.image_width, c.grid.gx, a.gy_view, c.H, c.grid.ntiles, c.header, c.work_order, c.tile_start,
         c.keys, c.geom, a.prm.bg, queue, a.out_color, a.out_depth_alpha, c.n_contrib, a.score, a.stats);
     return cudaGetLastError();
 }
@@ -949,13 +966,13 @@ static cudaError_t launch_fwd_tma(const GsrFwdArgs& a, int nblocks, const CompPt
 }
 
 cudaError_t gsr_launch_composite_fwd(const GsrFwdArgs& a) {
-    const CompPtrs c = comp_ptrs(a.saved, a.vl, a.prm.image_height, a.prm.image_width);
+    const CompPtrs c = comp_ptrs(a.saved, a.vl, a.prm.image_height, a.prm.image_width, a.num_views, a.gy_view);
     if (c.grid.ntiles == 0) return cudaSuccess;
     uint32_t* queue = reinterpret_cast<uint32_t*>(a.scratch + a.sl.counters) + GSR_C_FWD_QUEUE;
     const int nblocks = min(c.grid.ntiles, a.num_sms * 6);
     // B200GSR_FWD_VARIANT = 1 | 2: bulk-copy / TMA staging experiments (profiles/r02_tma_ab.md)
     static const int fwd_variant = [] { const char* e = getenv("B200GSR_FWD_VARIANT"); return e ? atoi(e) : 0; }();
-    if (fwd_variant != 0 && !a.prm.score_flag && a.stats == nullptr) {
+    if (fwd_variant != 0 && !a.prm.score_flag && a.stats == nullptr && a.num_views == 1) {
         const int nb = min(c.grid.ntiles, a.num_sms * 5);
         return fwd_variant == 2 ? launch_fwd_tma<2>(a, nb, c, queue) : launch_fwd_tma<1>(a, nb, c, queue);
     }
@@ -972,7 +989,7 @@ static cudaError_t launch_bwd(const GsrBwdArgs& a, const CompPtrs& c, uint32_t* 
     cudaError_t e = gsr_smem_once(composite_bwd_kernel<kSlots, kMinCtas>, smem, attr_done);
     if (e != cudaSuccess) return e;
     composite_bwd_kernel<kSlots, kMinCtas><<<nblocks, kWarps * 32, smem, a.stream>>>(
-        a.prm.image_height, a.prm.image_width, c.grid.gx, c.grid.ntiles, c.header, c.work_order, c.tile_start,
+        a.prm.image_height, a.prm.image_width, c.grid.gx, a.gy_view, c.H, c.grid.ntiles, c.header, c.work_order, c.tile_start,
         c.keys, c.geom, a.prm.bg, queue, a.out_depth_alpha, c.n_contrib, a.dL_dcolor, a.dL_ddepth_alpha, dgeom);
     return cudaGetLastError();
 }
@@ -985,14 +1002,14 @@ static cudaError_t launch_bwd2(const GsrBwdArgs& a, const CompPtrs& c, uint32_t*
     cudaError_t e = gsr_smem_once(composite_bwd2_kernel<kSlots, kMinCtas, KFAST, STATS>, smem, attr_done);
     if (e != cudaSuccess) return e;
     composite_bwd2_kernel<kSlots, kMinCtas, KFAST, STATS><<<nblocks, kWarps * 32, smem, a.stream>>>(
-        a.prm.image_height, a.prm.image_width, c.grid.gx, c.grid.ntiles, c.header, c.work_order, c.tile_start,
+        a.prm.image_height, a.prm.image_width, c.grid.gx, a.gy_view, c.H, c.grid.ntiles, c.header, c.work_order, c.tile_start,
         c.keys, c.geom, a.prm.bg, queue, a.out_depth_alpha, c.n_contrib, a.dL_dcolor, a.dL_ddepth_alpha, dgeom,
         a.stats);
     return cudaGetLastError();
 }
 
 cudaError_t gsr_launch_composite_bwd(const GsrBwdArgs& a) {
-    const CompPtrs c = comp_ptrs(a.saved, a.vl, a.prm.image_height, a.prm.image_width);
+    const CompPtrs c = comp_ptrs(a.saved, a.vl, a.prm.image_height, a.prm.image_width, a.num_views, a.gy_view);
     if (c.grid.ntiles == 0) return cudaSuccess;
     uint32_t* queue = reinterpret_cast<uint32_t*>(a.saved + a.vl.header) + GSR_H_BWD_QUEUE;
     float* dgeom = reinterpret_cast<float*>(a.saved + a.vl.dgeom);

@@ -269,7 +269,8 @@ project_sh_kernel(b200gsr_params p, const float* __restrict__ means3D,
                   const float* __restrict__ rots, const float* __restrict__ cov3d,
                   int32_t* __restrict__ radii, uint4* __restrict__ rectdepth,
                   GsrRec* __restrict__ geom, uint32_t* __restrict__ tile_count,
-                  uint32_t* __restrict__ zero_words, int num_zero_words, float* __restrict__ dgeom) {
+                  uint32_t* __restrict__ zero_words, int num_zero_words, float* __restrict__ dgeom,
+                  int rec_base, int tile_row_off, int ntiles_total) {
     extern __shared__ __align__(16) float sh_buf[];
     __shared__ uint8_t vis_s[kBlock];
     const int g0 = blockIdx.x * kBlock;
@@ -316,8 +317,13 @@ project_sh_kernel(b200gsr_params p, const float* __restrict__ means3D,
                 }
             }
         }
-        radii[i] = radius;
-        rectdepth[i] = rd;
+        if (vis) {      // multi-view: this view's rows of the vertically stacked image
+            rd.x += (uint32_t)tile_row_off << 16;
+            rd.y += (uint32_t)tile_row_off << 16;
+            miny += tile_row_off; maxy += tile_row_off;
+        }
+        radii[rec_base + i] = radius;
+        rectdepth[rec_base + i] = rd;
     }
     const int stride = sh_row_stride(p.M);
     const int ncoef = (p.sh_degree + 1) * (p.sh_degree + 1);
@@ -331,8 +337,8 @@ project_sh_kernel(b200gsr_params p, const float* __restrict__ means3D,
 
     // fallback binning only (tile grid too large for the smem multisplit): privatised global
     // tile counters; the RED atomics overlap the colour math below
-    if (!gsr_use_multisplit(grid.ntiles)) {
-        uint32_t* cnt = tile_count + (size_t)((i >> 5) & (GSR_COPIES - 1)) * grid.ntiles;
+    if (!gsr_use_multisplit(ntiles_total)) {
+        uint32_t* cnt = tile_count + (size_t)(((rec_base + i) >> 5) & (GSR_COPIES - 1)) * ntiles_total;
         for (int ty = miny; ty < maxy; ++ty)
             for (int tx = minx; tx < maxx; ++tx) atomicAdd(cnt + ty * grid.gx + tx, 1u);
     }
@@ -363,7 +369,7 @@ project_sh_kernel(b200gsr_params p, const float* __restrict__ means3D,
     }
     const __half2 eh = __floats2half2_rn(ex, ey);
     GsrRec rec;
-    rec.px = g.px; rec.py = g.py;
+    rec.px = g.px; rec.py = g.py;      // view-local pixel coordinates (the composite kernels evaluate view-locally too)
 #ifdef GSR_EXACT_EXP
     rec.A = MUL(g.c, g.det_inv);                      // raw conic (x, y, z) as the oracle forms it
     rec.B = MUL(-g.b, g.det_inv);
@@ -373,14 +379,14 @@ project_sh_kernel(b200gsr_params p, const float* __restrict__ means3D,
     rec.B = GSR_LOG2E * MUL(g.b, g.det_inv);          // -log2e * conic.y, conic.y = -b/det
     rec.C = -0.5f * GSR_LOG2E * MUL(g.a, g.det_inv);
 #endif
-    rec.opacity = o; rec.depth = g.tz; rec.idx = (uint32_t)i;
+    rec.opacity = o; rec.depth = g.tz; rec.idx = (uint32_t)(rec_base + i);
     rec.r = rgb[0]; rec.g = rgb[1]; rec.b = rgb[2];
     rec.ext = *reinterpret_cast<const uint32_t*>(&eh);
-    float4* dst = reinterpret_cast<float4*>(geom + i);
+    float4* dst = reinterpret_cast<float4*>(geom + rec_base + i);
     const float4* src = reinterpret_cast<const float4*>(&rec);
     dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
     if (dgeom != nullptr) {   // gradient accumulators of this (visible) Gaussian start at zero
-        float4* dz = reinterpret_cast<float4*>(dgeom + 12 * (size_t)i);
+        float4* dz = reinterpret_cast<float4*>(dgeom + 12 * (size_t)(rec_base + i));
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         dz[0] = z4; dz[1] = z4; dz[2] = z4;
     }
@@ -399,7 +405,7 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
                    const float* __restrict__ scales, const float* __restrict__ rots,
                    const float* __restrict__ cov3d, const int32_t* __restrict__ radii,
                    float* __restrict__ dgeom, uint32_t* __restrict__ bwd_queue,
-                   int g_base, int g_end, int dsh_coefs,
+                   int g_base, int g_end, int dsh_coefs, int rec_base, int accumulate,
                    float* __restrict__ d_means3D, float* __restrict__ d_means2D,
                    float* __restrict__ d_shs, float* __restrict__ d_colors,
                    float* __restrict__ d_opac, float* __restrict__ d_scales,
@@ -411,7 +417,7 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
     const int g0 = g_base + blockIdx.x * kBlock;
     const int i = g0 + threadIdx.x;
     const bool active = i < g_end;
-    const bool vis = active && (__ldg(radii + i) > 0);
+    const bool vis = active && (__ldg(radii + rec_base + i) > 0);
     const int nsh = 3 * dsh_coefs;          // floats per row of d_shs: 3*M (reference layout) or compact
     const int stride = sh_row_stride(p.M);
     const int deg = p.sh_degree;
@@ -430,7 +436,7 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
     float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float dcol[3] = {0.f, 0.f, 0.f};
     // composite_bwd (the previous kernel on the stream) has drained its work queue: reset it
-    if (g_base == 0 && blockIdx.x == 0 && threadIdx.x < GSR_NQUEUE) bwd_queue[threadIdx.x] = 0u;
+    if (g_base == 0 && rec_base == 0 && blockIdx.x == 0 && threadIdx.x < GSR_NQUEUE) bwd_queue[threadIdx.x] = 0u;
 
     if (vis) {
         Cam C;
@@ -441,7 +447,7 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
         geo_view(C, x, y, z, g);
         geo_rest(C, p, x, y, z, scales, rots, cov3d, i, g);
         // read-and-clear: the accumulators are zero again for the next backward over this `saved`
-        float4* dg = reinterpret_cast<float4*>(dgeom + 12 * (size_t)i);
+        float4* dg = reinterpret_cast<float4*>(dgeom + 12 * (size_t)(rec_base + i));
         const float4 a0 = dg[0], a1 = dg[1], a2 = dg[2];
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         dg[0] = z4; dg[1] = z4; dg[2] = z4;
@@ -611,20 +617,29 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
         }
     }
 
-    // ---- dense writes (zeros for culled Gaussians) ---------------------------------------
+    // ---- dense writes (zeros for culled Gaussians).  `accumulate` (bit per output: 1 means3D, 2 opacity,
+    // 4 sh/colour, 8 scales, 16 rotations, 32 cov3D) adds into the output instead: later views of a multi-view
+    // backward that share the parameter with an earlier view.
+#define GSR_OUT(ptr, val, bit) do { float* p_ = (ptr); *p_ = (accumulate & (bit)) ? *p_ + (val) : (val); } while (0)
     if (active) {
-        d_means3D[3 * (size_t)i] = dmean[0]; d_means3D[3 * (size_t)i + 1] = dmean[1]; d_means3D[3 * (size_t)i + 2] = dmean[2];
+        GSR_OUT(d_means3D + 3 * (size_t)i, dmean[0], 1); GSR_OUT(d_means3D + 3 * (size_t)i + 1, dmean[1], 1);
+        GSR_OUT(d_means3D + 3 * (size_t)i + 2, dmean[2], 1);
         d_means2D[3 * (size_t)i] = dm2[0]; d_means2D[3 * (size_t)i + 1] = dm2[1]; d_means2D[3 * (size_t)i + 2] = 0.f;
-        d_opac[i] = dop;
+        GSR_OUT(d_opac + i, dop, 2);
         if (cov3d != nullptr) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) d_cov3d[6 * (size_t)i + k] = dcov[k];
+            for (int k = 0; k < 6; ++k) GSR_OUT(d_cov3d + 6 * (size_t)i + k, dcov[k], 32);
         } else {
-            d_scales[3 * (size_t)i] = dsc[0]; d_scales[3 * (size_t)i + 1] = dsc[1]; d_scales[3 * (size_t)i + 2] = dsc[2];
-            reinterpret_cast<float4*>(d_rots)[i] = make_float4(drot[0], drot[1], drot[2], drot[3]);
+            GSR_OUT(d_scales + 3 * (size_t)i, dsc[0], 8); GSR_OUT(d_scales + 3 * (size_t)i + 1, dsc[1], 8);
+            GSR_OUT(d_scales + 3 * (size_t)i + 2, dsc[2], 8);
+            float4* dr = reinterpret_cast<float4*>(d_rots) + i;
+            float4 rv = make_float4(drot[0], drot[1], drot[2], drot[3]);
+            if (accumulate & 16) { const float4 o = *dr; rv.x += o.x; rv.y += o.y; rv.z += o.z; rv.w += o.w; }
+            *dr = rv;
         }
         if (shs == nullptr) {
-            d_colors[3 * (size_t)i] = dcol[0]; d_colors[3 * (size_t)i + 1] = dcol[1]; d_colors[3 * (size_t)i + 2] = dcol[2];
+            GSR_OUT(d_colors + 3 * (size_t)i, dcol[0], 4); GSR_OUT(d_colors + 3 * (size_t)i + 1, dcol[1], 4);
+            GSR_OUT(d_colors + 3 * (size_t)i + 2, dcol[2], 4);
         }
     }
     if (shs != nullptr) {
@@ -638,7 +653,8 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
             float* base = d_shs + (size_t)g0 * nsh;
             for (int f = threadIdx.x; f < rows * nsh; f += kBlock) {
                 const int row = f / nsh, col = f - row * nsh;
-                base[f] = (vis_s[row] && col < nf) ? sh_buf[row * stride + col] : 0.0f;
+                const float val = (vis_s[row] && col < nf) ? sh_buf[row * stride + col] : 0.0f;
+                base[f] = (accumulate & 4) ? base[f] + val : val;
             }
         } else if (MT > 0 && ((3 * MT) & 3) == 0) {
             constexpr int q4 = (3 * (MT > 0 ? MT : 4)) / 4;
@@ -650,6 +666,10 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
                 if (g0 + row < g_end) {
                     float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (c4 < nchunk && vis_s[row]) val = *reinterpret_cast<const float4*>(sh_buf + row * stride + 4 * c4);
+                    if (accumulate & 4) {
+                        const float4 o = ldg_f4(base + 4 * u);
+                        val.x += o.x; val.y += o.y; val.z += o.z; val.w += o.w;
+                    }
                     stg_na_f4(base + 4 * u, val);
                 }
             }
@@ -666,11 +686,17 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
                     for (int q = hl; 4 * q < nsh; q += 16) {
                         float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (v && q < nchunk) val = *reinterpret_cast<const float4*>(sh_buf + row * stride + 4 * q);
+                        if (accumulate & 4) {
+                            const float4 o = ldg_f4(dst + 4 * q);
+                            val.x += o.x; val.y += o.y; val.z += o.z; val.w += o.w;
+                        }
                         stg_na_f4(dst + 4 * q, val);
                     }
                 } else {
-                    for (int col = hl; col < nsh; col += 16)
-                        dst[col] = (v && col < nf) ? sh_buf[row * stride + col] : 0.0f;
+                    for (int col = hl; col < nsh; col += 16) {
+                        const float val = (v && col < nf) ? sh_buf[row * stride + col] : 0.0f;
+                        dst[col] = (accumulate & 4) ? dst[col] + val : val;
+                    }
                 }
             }
         }
@@ -692,7 +718,8 @@ template <int MT>
 static void launch_project_sh(const GsrFwdArgs& a, int P, size_t smem) {
     // multisplit path: counters + the single per-tile counter array are zeroed in the prologue
     // (api.cu issues a memset instead on the large-grid fallback, where this kernel counts itself)
-    const GsrTileGrid tg = gsr_grid(a.prm.image_height, a.prm.image_width);
+    GsrTileGrid tg = gsr_grid(a.prm.image_height, a.prm.image_width);
+    tg.gy = a.num_views * a.gy_view; tg.ntiles = tg.gx * tg.gy;      // the stacked image
     const int nzero = gsr_use_multisplit(tg.ntiles)
         ? (int)((a.sl.tile_count + (size_t)tg.ntiles * sizeof(uint32_t)) / sizeof(uint32_t)) : 0;
     project_sh_kernel<MT><<<(P + kBlock - 1) / kBlock, kBlock, smem, a.stream>>>(
@@ -701,7 +728,8 @@ static void launch_project_sh(const GsrFwdArgs& a, int P, size_t smem) {
         reinterpret_cast<GsrRec*>(a.saved + a.vl.geom),
         reinterpret_cast<uint32_t*>(a.scratch + a.sl.tile_count),
         reinterpret_cast<uint32_t*>(a.scratch), nzero,
-        (a.flags & B200GSR_FWD_NO_BACKWARD) ? nullptr : reinterpret_cast<float*>(a.saved + a.vl.dgeom));
+        (a.flags & B200GSR_FWD_NO_BACKWARD) ? nullptr : reinterpret_cast<float*>(a.saved + a.vl.dgeom),
+        a.view * a.P_view, a.view * a.gy_view, tg.ntiles);
 }
 
 cudaError_t gsr_launch_project(const GsrFwdArgs& a) {
@@ -720,7 +748,7 @@ static void launch_project_bwd(const GsrBwdArgs& a, int g_begin, int g_end, size
         a.prm, a.means3D, a.shs, a.colors, a.scales, a.rots, a.cov3d, a.radii,
         reinterpret_cast<float*>(a.saved + a.vl.dgeom),
         reinterpret_cast<uint32_t*>(a.saved + a.vl.header) + GSR_H_BWD_QUEUE, g_begin, g_end,
-        a.dsh_coefs > 0 ? a.dsh_coefs : a.prm.M, a.d_means3D, a.d_means2D, a.d_shs,
+        a.dsh_coefs > 0 ? a.dsh_coefs : a.prm.M, a.view * a.P_view, a.accumulate, a.d_means3D, a.d_means2D, a.d_shs,
         a.d_colors, a.d_opac, a.d_scales, a.d_rots, a.d_cov3d);
 }
 

@@ -230,6 +230,72 @@ def _layouts(P, H, W, cap, with_backward):
     return r
 
 
+def _issue_with_capacity(d: _Device, dev, key, P_eff: int, H_eff: int, W: int, with_backward: bool, score, launch):
+    """The pair-capacity protocol shared by the single- and multi-view forwards.  `launch(cap, scratch,
+    saved, notify_ptr, seq)` enqueues the whole forward and returns the C return code; this helper
+    sizes the buffers, decides whether to wait for the device's pair count (sync mode / unknown
+    capacity) and re-issues on overflow.  -> (saved tensor, capacity)."""
+    capturing = torch.cuda.is_current_stream_capturing()
+    stream_h = torch.cuda.current_stream(dev).cuda_stream
+    known = d.capacity > 0 and (d.user_capacity or d.cap_key == key)
+    if capturing and d.capacity > 0:
+        known = True                   # cannot wait inside a capture: trust the high-water mark
+    if capturing and not known:
+        raise RuntimeError("b200gsr: capturing into a CUDA graph needs a known pair capacity: run one eager "
+                           "forward on this device first or call set_workspace_capacity()")
+    cap = _round_cap(max(d.capacity, _MIN_PAIRS_PER_GAUSSIAN * P_eff)) if known else _round_cap(6 * P_eff)
+    # wait for the count only when it is needed: sync mode, or the capacity is a blind first guess
+    wait = (not capturing) and (_pair_mode == "sync" or not known)
+    while True:
+        scratch_bytes, saved_bytes = _layouts(P_eff, H_eff, W, cap, with_backward)
+        scratch = d.ensure_scratch(stream_h, scratch_bytes)
+        saved = torch.empty(saved_bytes, dtype=torch.uint8, device=dev)
+        slot, seq, notify_ptr = -1, 0, None
+        if not capturing:
+            if not d.free_slots:
+                _resolve_pending(d, block=True)
+            slot, seq = d.free_slots.pop(), d.next_seq()
+            notify_ptr = C.c_void_p(d.notify.data_ptr() + 16 * slot)
+        rc = launch(cap, scratch, saved, notify_ptr, seq)
+        if rc:
+            if slot >= 0:
+                d.free_slots.append(slot)
+            msg = _lib.last_error()
+            if rc == -1:
+                raise Exception(msg)
+            raise RuntimeError(f"b200gsr_forward failed ({rc}): {msg}")
+        if capturing:
+            break
+        if not wait:
+            d.pending.append((slot, seq, cap))       # resolved lazily, never blocks the host
+            break
+        # Wait only for the tile scan (project + count + scan kernels); sort/composite keep running.
+        t0 = time.perf_counter()
+        n = d.notify_np
+        while int(n[slot, 0]) != seq:
+            if time.perf_counter() - t0 > _POLL_TIMEOUT_S:
+                torch.cuda.synchronize(dev)
+                if int(n[slot, 0]) == seq:
+                    break
+                raise RuntimeError("b200gsr_forward: device never reported the pair count")
+        pairs = int(n[slot, 1]) & 0xFFFFFFFF
+        d.free_slots.append(slot)
+        d.last_pairs = pairs
+        if pairs <= cap:
+            # high-water mark with 2x head-room: capacity only costs 8 B per pair in `saved`, and
+            # views of one training step differ a lot in pair count (random cameras).  A new
+            # shape starts its own high-water mark.
+            if not d.user_capacity:
+                fresh = d.cap_key != key
+                d.capacity = _round_cap(2 * pairs) if fresh else max(d.capacity, _round_cap(2 * pairs))
+                d.cap_key = key
+            break
+        cap = d.capacity = _round_cap(2 * pairs)   # overflow: re-issue with enough room
+        if score is not None:
+            score.zero_()
+    return saved, cap
+
+
 def _forward_impl(rs, means3D, shs, colors, opac, scales, rots, cov3d, with_backward=True):
     lib = _lib.load()
     dev = means3D.device
@@ -240,8 +306,7 @@ def _forward_impl(rs, means3D, shs, colors, opac, scales, rots, cov3d, with_back
     M = int(shs.shape[1]) if shs is not None else 0
     H, W = int(rs.image_height), int(rs.image_width)
     d = _device_state(dev)
-    capturing = torch.cuda.is_current_stream_capturing()
-    if not capturing:
+    if not torch.cuda.is_current_stream_capturing():
         d.ensure_notify()
         _resolve_pending(d)               # non-blocking: may raise PairCapacityOverflow for an earlier call
     keep: list = []
@@ -251,68 +316,16 @@ def _forward_impl(rs, means3D, shs, colors, opac, scales, rots, cov3d, with_back
         depth_alpha = torch.empty(2, H, W, dtype=torch.float32, device=dev)
         radii = torch.empty(P, dtype=torch.int32, device=dev)
         score = torch.zeros(P, dtype=torch.float32, device=dev) if rs.score_flag else None
-        stream_h = torch.cuda.current_stream(dev).cuda_stream
-        stream = C.c_void_p(stream_h)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         flags = 0 if with_backward else _lib.FWD_NO_BACKWARD
-        known = d.capacity > 0 and (d.user_capacity or d.cap_key == (P, H, W))
-        if capturing and d.capacity > 0:
-            known = True                   # cannot wait inside a capture: trust the high-water mark
-        if capturing and not known:
-            raise RuntimeError("b200gsr: capturing into a CUDA graph needs a known pair capacity: run one eager "
-                               "forward on this device first or call set_workspace_capacity()")
-        cap = _round_cap(max(d.capacity, _MIN_PAIRS_PER_GAUSSIAN * P)) if known else _round_cap(6 * P)
-        # wait for the count only when it is needed: sync mode, or the capacity is a blind first guess
-        wait = (not capturing) and (_pair_mode == "sync" or not known)
-        while True:
-            scratch_bytes, saved_bytes = _layouts(P, H, W, cap, with_backward)
-            scratch = d.ensure_scratch(stream_h, scratch_bytes)
-            saved = torch.empty(saved_bytes, dtype=torch.uint8, device=dev)
-            slot, seq, notify_ptr = -1, 0, None
-            if not capturing:
-                if not d.free_slots:
-                    _resolve_pending(d, block=True)
-                slot, seq = d.free_slots.pop(), d.next_seq()
-                notify_ptr = C.c_void_p(d.notify.data_ptr() + 16 * slot)
-            rc = lib.b200gsr_forward(C.byref(prm), _ptr(means3D), _ptr(shs), _ptr(colors), _ptr(opac),
-                                     _ptr(scales), _ptr(rots), _ptr(cov3d), _ptr(color), _ptr(depth_alpha),
-                                     _ptr(radii), _ptr(score), _ptr(scratch), scratch.numel(), _ptr(saved),
-                                     saved.numel(), cap, flags, notify_ptr, seq, stream)
-            if rc:
-                if slot >= 0:
-                    d.free_slots.append(slot)
-                msg = _lib.last_error()
-                if rc == -1:
-                    raise Exception(msg)
-                raise RuntimeError(f"b200gsr_forward failed ({rc}): {msg}")
-            if capturing:
-                break
-            if not wait:
-                d.pending.append((slot, seq, cap))       # resolved lazily, never blocks the host
-                break
-            # Wait only for the tile scan (project + count + scan kernels); sort/composite keep running.
-            t0 = time.perf_counter()
-            n = d.notify_np
-            while int(n[slot, 0]) != seq:
-                if time.perf_counter() - t0 > _POLL_TIMEOUT_S:
-                    torch.cuda.synchronize(dev)
-                    if int(n[slot, 0]) == seq:
-                        break
-                    raise RuntimeError("b200gsr_forward: device never reported the pair count")
-            pairs = int(n[slot, 1]) & 0xFFFFFFFF
-            d.free_slots.append(slot)
-            d.last_pairs = pairs
-            if pairs <= cap:
-                # high-water mark with 2x head-room: capacity only costs 8 B per pair in `saved`, and
-                # views of one training step differ a lot in pair count (random cameras).  A new
-                # shape starts its own high-water mark.
-                if not d.user_capacity:
-                    fresh = d.cap_key != (P, H, W)
-                    d.capacity = _round_cap(2 * pairs) if fresh else max(d.capacity, _round_cap(2 * pairs))
-                    d.cap_key = (P, H, W)
-                break
-            cap = d.capacity = _round_cap(2 * pairs)   # overflow: re-issue with enough room
-            if score is not None:
-                score.zero_()
+
+        def launch(cap, scratch, saved, notify_ptr, seq):
+            return lib.b200gsr_forward(C.byref(prm), _ptr(means3D), _ptr(shs), _ptr(colors), _ptr(opac),
+                                       _ptr(scales), _ptr(rots), _ptr(cov3d), _ptr(color), _ptr(depth_alpha),
+                                       _ptr(radii), _ptr(score), _ptr(scratch), scratch.numel(), _ptr(saved),
+                                       saved.numel(), cap, flags, notify_ptr, seq, stream)
+
+        saved, cap = _issue_with_capacity(d, dev, (P, H, W), P, H, W, with_backward, score, launch)
     st = _State()
     st.params_keep = keep; st.P = P; st.M = M; st.capacity = cap; st.saved = saved; st.rs = rs
     st.with_backward = with_backward
@@ -351,6 +364,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             tensors.append(t if t is not None else torch.empty(0, device=means3D.device))
         ctx.save_for_backward(*tensors)
         ctx.mark_non_differentiable(radii)
+        ctx.set_materialize_grads(False)     # no zeros_like(radii) fill kernel per backward: absent grads arrive as None
         if raster_settings.score_flag:
             ctx.mark_non_differentiable(score)
             return score, color, radii, depth_alpha

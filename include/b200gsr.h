@@ -180,6 +180,42 @@ int b200gsr_backward_ex(const b200gsr_params* prm,
                         uint32_t stages, int32_t g_begin, int32_t g_end, int32_t dsh_coefs,
                         void* stream);
 
+/*
+ * Multi-view rendering (additive, no upstream equivalent): B views of the same image
+ * size and the same P in ONE tile-binning / sort / composite pass.  DreamScene renders C_batch_size = 4
+ * views per training step one after the other (/root/reference/training/scene_trainer.py:801-832).
+ *   prm[B]  : per-view constants; prm[v].bg must point into ONE contiguous device array [B,3]
+ *             (prm[v].bg = prm[0].bg + 3 v); P, M, image size, score_flag equal across views;
+ *             sh_degree, scale_modifier, cameras may differ per view.
+ *   in[B]   : per-view input pointers (any of them may repeat view 0's pointer = shared parameter).
+ *   outputs : the views are stacked vertically, each padded to whole tile rows:
+ *             out_color [3, Hs, W], out_depth_alpha [2, Hs, W] with Hs from b200gsr_views_geometry
+ *             (view v occupies rows [v*Hs/B, v*Hs/B + H)); radii [B,P]; score [B*P] (score_flag).
+ *   scratch / saved: sized with the layout queries for (B*P, Hs, W).
+ * Backward: dL_dcolor / dL_ddepth_alpha in the same stacked layout; out[B] holds per-view gradient
+ * destinations.  out[v].accumulate is a bit mask (1 means3D, 2 opacities, 4 shs/colors, 8 scales,
+ * 16 rotations, 32 cov3D): set a bit when that destination is shared with an EARLIER view and the
+ * view's contribution must be added instead of written (d_means2D is always per view).
+ */
+#define B200GSR_MAX_VIEWS 16
+typedef struct b200gsr_view_inputs {
+    const float *means3D, *shs, *colors_precomp, *opacities, *scales, *rotations, *cov3D_precomp;
+} b200gsr_view_inputs;
+typedef struct b200gsr_view_grads {
+    float *d_means3D, *d_means2D, *d_shs, *d_colors, *d_opacities, *d_scales, *d_rotations, *d_cov3D;
+    uint32_t accumulate;
+} b200gsr_view_grads;
+int b200gsr_views_geometry(int32_t B, int32_t H, int32_t W, int32_t* stacked_height);
+int b200gsr_forward_views(int32_t B, const b200gsr_params* prm, const b200gsr_view_inputs* in,
+                          float* out_color, float* out_depth_alpha, int32_t* radii, float* score,
+                          void* scratch, size_t scratch_bytes, void* saved, size_t saved_bytes,
+                          uint64_t max_pairs, uint32_t flags, uint32_t* host_notify, uint32_t notify_seq,
+                          void* stream);
+int b200gsr_backward_views(int32_t B, const b200gsr_params* prm, const b200gsr_view_inputs* in,
+                           const int32_t* radii, const float* out_depth_alpha, const float* dL_dcolor,
+                           const float* dL_ddepth_alpha, void* saved, size_t saved_bytes, uint64_t max_pairs,
+                           const b200gsr_view_grads* out, void* stream);
+
 /* Frustum test only (replaces _C.mark_visible; DreamScene never calls it): visible[P] bytes. */
 int b200gsr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
                          const float* projmatrix, uint8_t* visible, void* stream);
