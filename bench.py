@@ -83,6 +83,8 @@ class ClockSampler:
         self.idx, self.proc, self.path = gpu_index, None, None
 
     def start(self):
+        if os.environ.get("BENCH_NO_CLOCKS"):       # diagnostics only: does the sampler perturb the run?
+            return
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)

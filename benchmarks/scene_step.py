@@ -126,8 +126,7 @@ def render_views(groups, cams, dev, bg, aug=True):
     (in-kernel Philox noise), shared positions / opacities / rotations, batched fused disparity."""
     named = [{"_xyz": g["xyz"], "_opacity": g["opacity"], "_scaling": g["scaling"], "_rotation": g["rotation"],
               "_features_dc": g["f_dc"], "_features_rest": g["f_rest"]} for g in groups]
-    per_view = [assemble_scene(named, shs_aug=aug, scale_aug=aug, noise="fused") for _ in cams]
-    xyz, opacity, _, rots, _ = per_view[0]
+    xyz, opacity, scales_v, rots, shs_v = assemble_scene(named, shs_aug=aug, scale_aug=aug, noise="fused", views=len(cams))
     S = [GaussianRasterizationSettings(
         image_height=c.image_height, image_width=c.image_width, tanfovx=c.tanfovx, tanfovy=c.tanfovy, bg=bg,
         scale_modifier=1.0, viewmatrix=c.world_view_transform, projmatrix=c.full_proj_transform, sh_degree=1,
@@ -135,7 +134,7 @@ def render_views(groups, cams, dev, bg, aug=True):
     screens = [torch.zeros_like(xyz, requires_grad=True) for _ in cams]
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    outs = rasterize_views(S, xyz, opacity, shs=[p[4] for p in per_view], scales=[p[2] for p in per_view], rotations=rots,
+    outs = rasterize_views(S, xyz, opacity, shs=list(shs_v.unbind(0)), scales=list(scales_v.unbind(0)), rotations=rots,
                            means2D=screens)
     t1.record()
     da = torch.stack([o[2] for o in outs])                                  # [B,2,H,W]

@@ -99,8 +99,8 @@ def load():
     lib.b200gsr_dist2_scratch_bytes.restype = C.c_size_t
     lib.b200gsr_dist2_knn3.argtypes = [i32, vp, vp, vp, sz, vp]
     lib.b200gsr_dist2_knn3.restype = C.c_int
-    lib.b200gsr_assemble_forward.argtypes = [i32, C.POINTER(Group), i32, C.c_float, C.c_float, vp, vp, u64] + [vp] * 5 + [vp]
-    lib.b200gsr_assemble_backward.argtypes = [i32, C.POINTER(Group), C.POINTER(GroupGrad), i32, C.c_float, C.c_float,
+    lib.b200gsr_assemble_forward.argtypes = [i32, C.POINTER(Group), i32, i32, C.c_float, C.c_float, vp, vp, u64] + [vp] * 5 + [vp]
+    lib.b200gsr_assemble_backward.argtypes = [i32, C.POINTER(Group), C.POINTER(GroupGrad), i32, i32, C.c_float, C.c_float,
                                               vp, vp, u64] + [vp] * 5 + [vp]
     lib.b200gsr_assemble_forward.restype = lib.b200gsr_assemble_backward.restype = C.c_int
     lib.b200gsr_disparity_forward.argtypes = [i32, i32, vp, vp, vp, vp, vp]

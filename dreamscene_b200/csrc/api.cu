@@ -507,15 +507,16 @@ static int check_groups(int32_t num_groups, const b200gsr_group* groups, int32_t
     return B200GSR_OK;
 }
 
-int b200gsr_assemble_forward(int32_t num_groups, const b200gsr_group* groups, int32_t M, float shs_noise,
+int b200gsr_assemble_forward(int32_t num_groups, const b200gsr_group* groups, int32_t M, int32_t num_views, float shs_noise,
                              float scale_noise, const float* z_shs, const float* z_scales, uint64_t seed,
                              float* means3D, float* opacities, float* scales, float* rotations, float* shs,
                              void* stream) {
     int rc = check_groups(num_groups, groups, M);
     if (rc) return rc;
     if (!means3D || !opacities || !scales || !rotations || !shs) return fail(B200GSR_ERR_BAD_ARG, "null output pointer");
+    if (num_views < 1 || num_views > B200GSR_MAX_VIEWS) return fail(B200GSR_ERR_BAD_ARG, "num_views %d not in 1..%d", num_views, B200GSR_MAX_VIEWS);
     GSR_RANGE_PUSH("b200gsr.assemble_fwd");
-    rc = check_cuda(gsr_launch_assemble(false, num_groups, groups, nullptr, M, shs_noise, scale_noise, z_shs, z_scales,
+    rc = check_cuda(gsr_launch_assemble(false, num_groups, groups, nullptr, M, num_views, shs_noise, scale_noise, z_shs, z_scales,
                                         seed, means3D, opacities, scales, rotations, shs,
                                         static_cast<cudaStream_t>(stream)), "assemble_forward");
     GSR_RANGE_POP();
@@ -523,7 +524,7 @@ int b200gsr_assemble_forward(int32_t num_groups, const b200gsr_group* groups, in
 }
 
 int b200gsr_assemble_backward(int32_t num_groups, const b200gsr_group* groups, const b200gsr_group_grad* grads,
-                              int32_t M, float shs_noise, float scale_noise, const float* z_shs,
+                              int32_t M, int32_t num_views, float shs_noise, float scale_noise, const float* z_shs,
                               const float* z_scales, uint64_t seed, const float* d_means3D,
                               const float* d_opacities, const float* d_scales, const float* d_rotations,
                               const float* d_shs, void* stream) {
@@ -535,8 +536,9 @@ int b200gsr_assemble_backward(int32_t num_groups, const b200gsr_group* groups, c
                                 !grads[g].f_dc || (M > 1 && !grads[g].f_rest)))
             return fail(B200GSR_ERR_BAD_ARG, "group %d: null gradient pointer", g);
     if (!d_means3D || !d_opacities || !d_scales || !d_rotations || !d_shs) return fail(B200GSR_ERR_BAD_ARG, "null gradient input");
+    if (num_views < 1 || num_views > B200GSR_MAX_VIEWS) return fail(B200GSR_ERR_BAD_ARG, "num_views %d not in 1..%d", num_views, B200GSR_MAX_VIEWS);
     GSR_RANGE_PUSH("b200gsr.assemble_bwd");
-    rc = check_cuda(gsr_launch_assemble(true, num_groups, groups, grads, M, shs_noise, scale_noise, z_shs, z_scales, seed,
+    rc = check_cuda(gsr_launch_assemble(true, num_groups, groups, grads, M, num_views, shs_noise, scale_noise, z_shs, z_scales, seed,
                                         const_cast<float*>(d_means3D), const_cast<float*>(d_opacities),
                                         const_cast<float*>(d_scales), const_cast<float*>(d_rotations),
                                         const_cast<float*>(d_shs), static_cast<cudaStream_t>(stream)), "assemble_backward");

@@ -79,7 +79,7 @@ __device__ __forceinline__ float4 normal4(unsigned long long seed, uint32_t stre
     __sincosf(6.283185307179586f * u3, &s1, &c1);
     return make_float4(ra * c0, ra * s0, rb * c1, rb * s1);
 }
-enum { kStreamShs = 1, kStreamScales = 2 };
+enum { kStreamShs = 1u, kStreamScales = 2u };    // + 2 * view
 
 // noise factor helpers: value v, standard normal z, coefficient c (0.2**0.5), divisor d (1 or 4):
 // reference order  v + z * ((c * v) / d)
@@ -93,9 +93,13 @@ constexpr int kAsmBlock = 128;
 // forward: block = 128 packed rows; phase A one thread per Gaussian (11 floats), phase B the
 // block's SH rows as a flat span of floats (coalesced stores; float4 when 3M % 4 == 0)
 // =============================================================================================
+// B = number of views: `scales` is [B][P,3] and `shs` [B][P,M,3] (one independently augmented copy per view, the
+// raw parameters are read ONCE), means3D / opac / rots are written once; in the backward the per-view gradients of
+// scales / shs are summed over the views in registers and every leaf gradient is written once.  View v uses the
+// noise rows z[v] (caller's draws) or the Philox streams 2v+1 / 2v+2.
 template <bool BACKWARD>
 __global__ void __launch_bounds__(kAsmBlock)
-assemble_kernel(GroupTable tab, GroupGradTable gtab, int P, int M, float c_shs, float c_scale,
+assemble_kernel(GroupTable tab, GroupGradTable gtab, int P, int M, int B, float c_shs, float c_scale,
                 const float* __restrict__ z_shs, const float* __restrict__ z_scales, unsigned long long seed,
                 // forward outputs / backward incoming gradients (packed)
                 float* __restrict__ means3D, float* __restrict__ opac, float* __restrict__ scales,
@@ -109,28 +113,42 @@ assemble_kernel(GroupTable tab, GroupGradTable gtab, int P, int M, float c_shs, 
         const float sx = tab.scaling[g][3 * (size_t)l], sy = tab.scaling[g][3 * (size_t)l + 1], sz = tab.scaling[g][3 * (size_t)l + 2];
         const float4 q = *reinterpret_cast<const float4*>(tab.rotation[g] + 4 * (size_t)l);
         const float o = tab.opacity[g][l];
-        float zs[3] = {0.f, 0.f, 0.f};
-        if (c_scale != 0.0f) {
-            if (z_scales != nullptr) {
-                zs[0] = z_scales[3 * (size_t)i]; zs[1] = z_scales[3 * (size_t)i + 1]; zs[2] = z_scales[3 * (size_t)i + 2];
-            } else {
-                const float4 n = normal4(seed, kStreamScales, (unsigned long long)i);
-                zs[0] = n.x; zs[1] = n.y; zs[2] = n.z;
-            }
-        }
         const float e[3] = {expf(sx), expf(sy), expf(sz)};
         const float sig = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-o)));
         const float nrm = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(q.x, q.x), __fmul_rn(q.y, q.y)), __fmul_rn(q.z, q.z)), __fmul_rn(q.w, q.w))), 1e-12f);
+        float dsum[3] = {0.f, 0.f, 0.f};
+        for (int v = 0; v < B; ++v) {
+            float zs[3] = {0.f, 0.f, 0.f};
+            if (c_scale != 0.0f) {
+                if (z_scales != nullptr) {
+                    const float* zr = z_scales + ((size_t)v * P + i) * 3;
+                    zs[0] = zr[0]; zs[1] = zr[1]; zs[2] = zr[2];
+                } else {
+                    const float4 n = normal4(seed, kStreamScales + 2u * (uint32_t)v, (unsigned long long)i);
+                    zs[0] = n.x; zs[1] = n.y; zs[2] = n.z;
+                }
+            }
+            float* sv = scales + ((size_t)v * P + i) * 3;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (!BACKWARD) {
+                    sv[k] = (c_scale != 0.0f) ? fmaxf(aug(e[k], zs[k], c_scale, 4.0f), 0.0f) : e[k];
+                } else {
+                    float d = sv[k];
+                    if (c_scale != 0.0f) {
+                        // y = clamp(e + z*((c*e)/4), 0): dy/de = 1 + z*c/4 where the clamp is inactive
+                        const float y = aug(e[k], zs[k], c_scale, 4.0f);
+                        d = (y > 0.0f) ? d * (1.0f + zs[k] * (c_scale * 0.25f)) : 0.0f;
+                    }
+                    dsum[k] += d;
+                }
+            }
+        }
         if (!BACKWARD) {
             means3D[3 * (size_t)i] = tab.xyz[g][3 * (size_t)l];
             means3D[3 * (size_t)i + 1] = tab.xyz[g][3 * (size_t)l + 1];
             means3D[3 * (size_t)i + 2] = tab.xyz[g][3 * (size_t)l + 2];
             opac[i] = sig;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float v = (c_scale != 0.0f) ? fmaxf(aug(e[k], zs[k], c_scale, 4.0f), 0.0f) : e[k];
-                scales[3 * (size_t)i + k] = v;
-            }
             *reinterpret_cast<float4*>(rots + 4 * (size_t)i) =
                 make_float4(__fdiv_rn(q.x, nrm), __fdiv_rn(q.y, nrm), __fdiv_rn(q.z, nrm), __fdiv_rn(q.w, nrm));
         } else {
@@ -140,15 +158,7 @@ assemble_kernel(GroupTable tab, GroupGradTable gtab, int P, int M, float c_shs, 
             gtab.xyz[g][3 * (size_t)l + 2] = means3D[3 * (size_t)i + 2];
             gtab.opacity[g][l] = opac[i] * sig * (1.0f - sig);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                float d = scales[3 * (size_t)i + k];
-                if (c_scale != 0.0f) {
-                    // y = clamp(e + z*((c*e)/4), 0): dy/de = 1 + z*c/4 where the clamp is inactive
-                    const float y = aug(e[k], zs[k], c_scale, 4.0f);
-                    d = (y > 0.0f) ? d * (1.0f + zs[k] * (c_scale * 0.25f)) : 0.0f;
-                }
-                gtab.scaling[g][3 * (size_t)l + k] = d * e[k];
-            }
+            for (int k = 0; k < 3; ++k) gtab.scaling[g][3 * (size_t)l + k] = dsum[k] * e[k];
             const float4 gq = *reinterpret_cast<const float4*>(rots + 4 * (size_t)i);
             const float inv = 1.0f / nrm;
             const float4 u = make_float4(q.x * inv, q.y * inv, q.z * inv, q.w * inv);
@@ -162,7 +172,8 @@ assemble_kernel(GroupTable tab, GroupGradTable gtab, int P, int M, float c_shs, 
     const int rows = min(kAsmBlock, P - r0);
     if (rows <= 0) return;
     const int row_f = 3 * M;
-    const size_t base = (size_t)r0 * row_f;          // first float of the block's span in the packed array
+    const size_t base = (size_t)r0 * row_f;          // first float of the block's span in one view's packed array
+    const size_t view_f = (size_t)P * row_f;         // floats per view
     const int total = rows * row_f;
     const bool vec = (row_f & 3) == 0;
     const int step = vec ? 4 : 1;
@@ -171,38 +182,53 @@ assemble_kernel(GroupTable tab, GroupGradTable gtab, int P, int M, float c_shs, 
         const int gi = r0 + row;
         const int g = find_group(tab, gi);
         const size_t l = (size_t)(gi - tab.start[g]);
-        float z[4] = {0.f, 0.f, 0.f, 0.f};
-        if (c_shs != 0.0f) {
-            if (z_shs != nullptr) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) if (k < step) z[k] = z_shs[base + f + k];
-            } else if (vec) {
-                const float4 n = normal4(seed, kStreamShs, (unsigned long long)((base + f) >> 2));
-                z[0] = n.x; z[1] = n.y; z[2] = n.z; z[3] = n.w;
-            } else {
-                const unsigned long long e = base + f;
-                const float4 n = normal4(seed, kStreamShs, e >> 2);
-                z[0] = (e & 3) == 0 ? n.x : (e & 3) == 1 ? n.y : (e & 3) == 2 ? n.z : n.w;
-            }
-        }
-        float out[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (k >= step) break;
-            const int c = col + k;
-            if (!BACKWARD) {
-                const float v = (c < 3) ? tab.f_dc[g][3 * l + c] : tab.f_rest[g][(size_t)(row_f - 3) * l + (c - 3)];
-                out[k] = (c_shs != 0.0f) ? aug(v, z[k], c_shs, 1.0f) : v;
-            } else {
-                float d = shs[base + f + k];
-                if (c_shs != 0.0f) d *= (1.0f + z[k] * c_shs);           // d(v + z*(c*v))/dv
-                if (c < 3) gtab.f_dc[g][3 * l + c] = d;
-                else gtab.f_rest[g][(size_t)(row_f - 3) * l + (c - 3)] = d;
-            }
-        }
+        float raw[4] = {0.f, 0.f, 0.f, 0.f}, dsum[4] = {0.f, 0.f, 0.f, 0.f};
         if (!BACKWARD) {
-            if (vec) *reinterpret_cast<float4*>(shs + base + f) = make_float4(out[0], out[1], out[2], out[3]);
-            else shs[base + f] = out[0];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (k >= step) break;
+                const int c = col + k;
+                raw[k] = (c < 3) ? tab.f_dc[g][3 * l + c] : tab.f_rest[g][(size_t)(row_f - 3) * l + (c - 3)];
+            }
+        }
+        for (int v = 0; v < B; ++v) {
+            float z[4] = {0.f, 0.f, 0.f, 0.f};
+            const size_t e0 = base + f;                          // element index inside the view
+            if (c_shs != 0.0f) {
+                if (z_shs != nullptr) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) if (k < step) z[k] = z_shs[(size_t)v * view_f + e0 + k];
+                } else {
+                    const float4 n = normal4(seed, kStreamShs + 2u * (uint32_t)v, (unsigned long long)(e0 >> 2));
+                    if (vec) { z[0] = n.x; z[1] = n.y; z[2] = n.z; z[3] = n.w; }
+                    else z[0] = (e0 & 3) == 0 ? n.x : (e0 & 3) == 1 ? n.y : (e0 & 3) == 2 ? n.z : n.w;
+                }
+            }
+            float* sv = shs + (size_t)v * view_f + e0;
+            if (!BACKWARD) {
+                float out[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) out[k] = (c_shs != 0.0f) ? aug(raw[k], z[k], c_shs, 1.0f) : raw[k];
+                if (vec) *reinterpret_cast<float4*>(sv) = make_float4(out[0], out[1], out[2], out[3]);
+                else sv[0] = out[0];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k >= step) break;
+                    float d = sv[k];
+                    if (c_shs != 0.0f) d *= (1.0f + z[k] * c_shs);           // d(v + z*(c*v))/dv
+                    dsum[k] += d;
+                }
+            }
+        }
+        if (BACKWARD) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (k >= step) break;
+                const int c = col + k;
+                if (c < 3) gtab.f_dc[g][3 * l + c] = dsum[k];
+                else gtab.f_rest[g][(size_t)(row_f - 3) * l + (c - 3)] = dsum[k];
+            }
         }
     }
 }
@@ -210,7 +236,7 @@ assemble_kernel(GroupTable tab, GroupGradTable gtab, int P, int M, float c_shs, 
 }  // namespace
 
 cudaError_t gsr_launch_assemble(bool backward, int num_groups, const b200gsr_group* groups,
-                                const b200gsr_group_grad* grads, int M, float c_shs, float c_scale,
+                                const b200gsr_group_grad* grads, int M, int B, float c_shs, float c_scale,
                                 const float* z_shs, const float* z_scales, unsigned long long seed,
                                 float* means3D, float* opac, float* scales, float* rots, float* shs, cudaStream_t s) {
     GroupTable tab;
@@ -233,10 +259,10 @@ cudaError_t gsr_launch_assemble(bool backward, int num_groups, const b200gsr_gro
     if (P == 0) return cudaSuccess;
     const int nblocks = (P + kAsmBlock - 1) / kAsmBlock;
     if (backward)
-        assemble_kernel<true><<<nblocks, kAsmBlock, 0, s>>>(tab, gtab, P, M, c_shs, c_scale, z_shs, z_scales, seed,
+        assemble_kernel<true><<<nblocks, kAsmBlock, 0, s>>>(tab, gtab, P, M, B, c_shs, c_scale, z_shs, z_scales, seed,
                                                             means3D, opac, scales, rots, shs);
     else
-        assemble_kernel<false><<<nblocks, kAsmBlock, 0, s>>>(tab, gtab, P, M, c_shs, c_scale, z_shs, z_scales, seed,
+        assemble_kernel<false><<<nblocks, kAsmBlock, 0, s>>>(tab, gtab, P, M, B, c_shs, c_scale, z_shs, z_scales, seed,
                                                              means3D, opac, scales, rots, shs);
     return cudaGetLastError();
 }

@@ -196,7 +196,7 @@ cudaError_t gsr_launch_mark_visible(int P, const float* means3D, const float* vi
 
 // scene assembly (assemble.cu)
 cudaError_t gsr_launch_assemble(bool backward, int num_groups, const b200gsr_group* groups,
-                                const b200gsr_group_grad* grads, int M, float c_shs, float c_scale,
+                                const b200gsr_group_grad* grads, int M, int B, float c_shs, float c_scale,
                                 const float* z_shs, const float* z_scales, unsigned long long seed,
                                 float* means3D, float* opac, float* scales, float* rots, float* shs, cudaStream_t s);
 

@@ -76,8 +76,9 @@ struct PairEval {
 __device__ __forceinline__ PairEval eval_pair(float px, float py, float A, float B, float C,
                                               float opacity, float X, float Y) {
     PairEval e;
-    e.dx = __fsub_rn(px, X);
-    e.dy = __fsub_rn(py, Y);
+    const float2 d2 = __fadd2_rn(make_float2(px, py), make_float2(-X, -Y));     // one FADD2
+    e.dx = d2.x;
+    e.dy = d2.y;
 #ifdef GSR_EXACT_EXP
     // oracle order (splat_ref.py::composite): power = -0.5*(A*dx*dx + C*dy*dy) - B*dx*dy, raw conic
     const float qs = __fadd_rn(__fmul_rn(__fmul_rn(A, e.dx), e.dx), __fmul_rn(__fmul_rn(C, e.dy), e.dy));
@@ -165,7 +166,8 @@ composite_fwd_kernel(int H, int W, int gx, int gy_view, int Hs, int ntiles, cons
         const int Xi = X0i + (lane & 7), Yi = Y0i + (lane >> 3);
         const float X0 = (float)X0i, Y0 = (float)Y0i, X = (float)Xi;
         bool inside[PPL], done[PPL];
-        float Y[PPL], T[PPL], Cr[PPL], Cg[PPL], Cb[PPL], Dacc[PPL];
+        float Y[PPL], T[PPL];
+        float2 C01[PPL], C2D[PPL];         // (r, g) and (b, depth) accumulators: two FFMA2 per blend
         uint32_t last[PPL];
         bool all_done = true;
 #pragma unroll
@@ -174,7 +176,7 @@ composite_fwd_kernel(int H, int W, int gx, int gy_view, int Hs, int ntiles, cons
             done[q] = !inside[q];
             all_done = all_done && done[q];
             Y[q] = (float)(Yi + 4 * q);
-            T[q] = 1.0f; Cr[q] = Cg[q] = Cb[q] = Dacc[q] = 0.f; last[q] = 0;
+            T[q] = 1.0f; C01[q] = make_float2(0.f, 0.f); C2D[q] = make_float2(0.f, 0.f); last[q] = 0;
         }
 
         // prologue: gather chunk 0, prefetch the keys of chunk 1
@@ -232,10 +234,9 @@ composite_fwd_kernel(int H, int W, int gx, int gy_view, int Hs, int ntiles, cons
                                 done[q] = true;
                             } else {
                                 const float wgt = e.alpha * T[q];
-                                Cr[q] = fmaf(q2.x, wgt, Cr[q]);
-                                Cg[q] = fmaf(q2.y, wgt, Cg[q]);
-                                Cb[q] = fmaf(q2.z, wgt, Cb[q]);
-                                Dacc[q] = fmaf(q1.w, wgt, Dacc[q]);
+                                const float2 w2 = make_float2(wgt, wgt);
+                                C01[q] = __ffma2_rn(make_float2(q2.x, q2.y), w2, C01[q]);
+                                C2D[q] = __ffma2_rn(make_float2(q2.z, q1.w), w2, C2D[q]);
                                 T[q] = Tn;
                                 last[q] = pos0 + (uint32_t)b;
                                 if (SCORE) wsum += wgt;
@@ -262,10 +263,10 @@ composite_fwd_kernel(int H, int W, int gx, int gy_view, int Hs, int ntiles, cons
         for (int q = 0; q < PPL; ++q) {
             if (inside[q]) {
                 const size_t pix = (size_t)(row0 + Yi + 4 * q) * W + Xi;
-                out_color[pix] = fmaf(T[q], bg0, Cr[q]);
-                out_color[plane + pix] = fmaf(T[q], bg1, Cg[q]);
-                out_color[2 * plane + pix] = fmaf(T[q], bg2, Cb[q]);
-                out_depth_alpha[pix] = Dacc[q];
+                out_color[pix] = fmaf(T[q], bg0, C01[q].x);
+                out_color[plane + pix] = fmaf(T[q], bg1, C01[q].y);
+                out_color[2 * plane + pix] = fmaf(T[q], bg2, C2D[q].x);
+                out_depth_alpha[pix] = C2D[q].y;
                 out_depth_alpha[plane + pix] = T[q];
                 n_contrib[pix] = last[q];
             }

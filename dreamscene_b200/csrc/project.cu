@@ -10,6 +10,7 @@
 // written in the oracle, so those integers are bit-exact against it.
 #include "common.cuh"
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 #define MUL(a, b) __fmul_rn((a), (b))
 #define ADD(a, b) __fadd_rn((a), (b))
@@ -72,10 +73,28 @@ __device__ __forceinline__ void geo_view(const Cam& C, float x, float y, float z
     g.tz = ADD(ADD(ADD(MUL(C.V[2], x), MUL(C.V[6], y)), MUL(C.V[10], z)), C.V[14]);
 }
 
+// raw per-Gaussian shape parameters, loadable ahead of the math (project_bwd issues these loads while
+// its SH rows are still in flight)
+struct RawShape {
+    float s[3];
+    float4 q;
+    float cov[6];
+};
+__device__ __forceinline__ void load_shape(const float* __restrict__ scales, const float* __restrict__ rots,
+                                           const float* __restrict__ cov3d, int i, RawShape& r) {
+    if (cov3d != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) r.cov[k] = __ldg(cov3d + 6 * (size_t)i + k);
+    } else {
+        r.s[0] = __ldg(scales + 3 * (size_t)i + 0);
+        r.s[1] = __ldg(scales + 3 * (size_t)i + 1);
+        r.s[2] = __ldg(scales + 3 * (size_t)i + 2);
+        r.q = __ldg(reinterpret_cast<const float4*>(rots) + i);
+    }
+}
+
 __device__ __forceinline__ void geo_rest(const Cam& C, const b200gsr_params& p, float x, float y,
-                                         float z, const float* __restrict__ scales,
-                                         const float* __restrict__ rots,
-                                         const float* __restrict__ cov3d, int i, Geo& g) {
+                                         float z, bool has_cov, const RawShape& raw, Geo& g) {
     g.hx = ADD(ADD(ADD(MUL(C.F[0], x), MUL(C.F[4], y)), MUL(C.F[8], z)), C.F[12]);
     g.hy = ADD(ADD(ADD(MUL(C.F[1], x), MUL(C.F[5], y)), MUL(C.F[9], z)), C.F[13]);
     g.hw = ADD(ADD(ADD(MUL(C.F[3], x), MUL(C.F[7], y)), MUL(C.F[11], z)), C.F[15]);
@@ -85,15 +104,15 @@ __device__ __forceinline__ void geo_rest(const Cam& C, const b200gsr_params& p, 
     g.px = MUL(SUB(MUL(ADD(ndcx, 1.0f), Wf), 1.0f), 0.5f);
     g.py = MUL(SUB(MUL(ADD(ndcy, 1.0f), Hf), 1.0f), 0.5f);
 
-    if (cov3d != nullptr) {
+    if (has_cov) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) g.S[k] = __ldg(cov3d + 6 * (size_t)i + k);
+        for (int k = 0; k < 6; ++k) g.S[k] = raw.cov[k];
     } else {
         const float mod = p.scale_modifier;
-        g.s[0] = MUL(mod, __ldg(scales + 3 * (size_t)i + 0));
-        g.s[1] = MUL(mod, __ldg(scales + 3 * (size_t)i + 1));
-        g.s[2] = MUL(mod, __ldg(scales + 3 * (size_t)i + 2));
-        const float4 q = __ldg(reinterpret_cast<const float4*>(rots) + i);
+        g.s[0] = MUL(mod, raw.s[0]);
+        g.s[1] = MUL(mod, raw.s[1]);
+        g.s[2] = MUL(mod, raw.s[2]);
+        const float4 q = raw.q;
         const float r = q.x, qx = q.y, qy = q.z, qz = q.w;
         g.R[0] = SUB(1.0f, MUL(2.0f, ADD(MUL(qy, qy), MUL(qz, qz))));
         g.R[1] = MUL(2.0f, SUB(MUL(qx, qy), MUL(r, qz)));
@@ -183,7 +202,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // MT > 0: M known at compile time (16 = objects, 4 = scenes) -> the block's rows are one contiguous
 // span of kBlock*3M floats that the threads copy as a flat sequence of 16-B units (perfectly
 // coalesced, constant-divisor index math).  MT == 0: generic M (half a warp per row).
-template <int MT>
+template <int MT, bool WAIT = true>
 __device__ __forceinline__ void stage_sh_rows(const float* __restrict__ shs, int M, int nf, int g0, int P,
                                               const uint8_t* vis, float* buf, int stride) {
     const int nchunk = (nf + 3) >> 2;
@@ -213,7 +232,8 @@ __device__ __forceinline__ void stage_sh_rows(const float* __restrict__ shs, int
             }
         }
     }
-    cp_async_wait_all();
+    if (WAIT) cp_async_wait_all();
+    else asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 // basis values for degree <= 3 at unit direction (x,y,z): utils/sh_utils.py:73-102
@@ -295,7 +315,10 @@ project_sh_kernel(b200gsr_params p, const float* __restrict__ means3D,
         geo_view(C, x, y, z, g);
         rd.z = __float_as_uint(g.tz);
         if (g.tz > GSR_NEAR_Z) {
-            geo_rest(C, p, x, y, z, scales, rots, cov3d, i, g);
+            // (hoisting these loads above the depth cull was measured: 0.0852 vs 0.0854 ms, no gain)
+            RawShape raw;
+            load_shape(scales, rots, cov3d, i, raw);
+            geo_rest(C, p, x, y, z, cov3d != nullptr, raw, g);
             if (g.det != 0.0f) {
                 const float mid = MUL(0.5f, ADD(g.a, g.c));
                 const float sq = SQRT(fmaxf(SUB(MUL(mid, mid), g.det), 0.1f));
@@ -398,8 +421,8 @@ project_sh_kernel(b200gsr_params p, const float* __restrict__ means3D,
 //   2: sum g*dx*dx  3: sum g*dx*dy  4: sum g*dy*dy
 //   5: sum G*dL/dalpha (dL/dopacity)   6..8: dL/drgb   9: dL/ddepth   10,11: unused
 // =========================================================================================
-template <int MT>
-__global__ void __launch_bounds__(kBlock, 8)
+template <int MT, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB)
 project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
                    const float* __restrict__ shs, const float* __restrict__ colors,
                    const float* __restrict__ scales, const float* __restrict__ rots,
@@ -425,7 +448,21 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
     if (shs != nullptr) {
         vis_s[threadIdx.x] = vis;
         __syncthreads();
-        stage_sh_rows<MT>(shs, p.M, 3 * ncoef, g0, g_end, vis_s, sh_buf, stride);
+        stage_sh_rows<MT, false>(shs, p.M, 3 * ncoef, g0, g_end, vis_s, sh_buf, stride);   // issue only
+    }
+    // every other global load of this thread is issued while the SH rows are still in flight
+    float x = 0.f, y = 0.f, z = 0.f;
+    RawShape raw;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
+    float4* dg = nullptr;
+    if (vis) {
+        x = __ldg(means3D + 3 * (size_t)i); y = __ldg(means3D + 3 * (size_t)i + 1); z = __ldg(means3D + 3 * (size_t)i + 2);
+        load_shape(scales, rots, cov3d, i, raw);
+        dg = reinterpret_cast<float4*>(dgeom + 12 * (size_t)(rec_base + i));
+        a0 = dg[0]; a1 = dg[1]; a2 = dg[2];
+    }
+    if (shs != nullptr) {
+        cp_async_wait_all();
         __syncthreads();
     }
     float dmean[3] = {0.f, 0.f, 0.f};
@@ -441,14 +478,10 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
     if (vis) {
         Cam C;
         load_cam(p, C);
-        const float x = __ldg(means3D + 3 * (size_t)i), y = __ldg(means3D + 3 * (size_t)i + 1),
-                    z = __ldg(means3D + 3 * (size_t)i + 2);
         Geo g;
         geo_view(C, x, y, z, g);
-        geo_rest(C, p, x, y, z, scales, rots, cov3d, i, g);
+        geo_rest(C, p, x, y, z, cov3d != nullptr, raw, g);
         // read-and-clear: the accumulators are zero again for the next backward over this `saved`
-        float4* dg = reinterpret_cast<float4*>(dgeom + 12 * (size_t)(rec_base + i));
-        const float4 a0 = dg[0], a1 = dg[1], a2 = dg[2];
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         dg[0] = z4; dg[1] = z4; dg[2] = z4;
         const float Wf = (float)p.image_width, Hf = (float)p.image_height;
@@ -537,7 +570,7 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
 #pragma unroll
                 for (int r_ = 0; r_ < 3; ++r_) dR[3 * r_ + c_] = dLm[3 * r_ + c_] * g.s[c_];
             }
-            const float4 q = __ldg(reinterpret_cast<const float4*>(rots) + i);
+            const float4 q = raw.q;
             const float r = q.x, qx = q.y, qy = q.z, qz = q.w;
             drot[0] = 2.f * (-qz * dR[1] + qy * dR[2] + qz * dR[3] - qx * dR[5] - qy * dR[6] + qx * dR[7]);
             drot[1] = 2.f * (qy * dR[1] + qz * dR[2] + qy * dR[3] - 2.f * qx * dR[4] - r * dR[5] +
@@ -742,14 +775,28 @@ cudaError_t gsr_launch_project(const GsrFwdArgs& a) {
     return cudaGetLastError();
 }
 
-template <int MT>
-static void launch_project_bwd(const GsrBwdArgs& a, int g_begin, int g_end, size_t smem) {
-    project_bwd_kernel<MT><<<(g_end - g_begin + kBlock - 1) / kBlock, kBlock, smem, a.stream>>>(
+template <int MT, int MINB>
+static void launch_project_bwd_v(const GsrBwdArgs& a, int g_begin, int g_end, size_t smem) {
+    project_bwd_kernel<MT, MINB><<<(g_end - g_begin + kBlock - 1) / kBlock, kBlock, smem, a.stream>>>(
         a.prm, a.means3D, a.shs, a.colors, a.scales, a.rots, a.cov3d, a.radii,
         reinterpret_cast<float*>(a.saved + a.vl.dgeom),
         reinterpret_cast<uint32_t*>(a.saved + a.vl.header) + GSR_H_BWD_QUEUE, g_begin, g_end,
         a.dsh_coefs > 0 ? a.dsh_coefs : a.prm.M, a.view * a.P_view, a.accumulate, a.d_means3D, a.d_means2D, a.d_shs,
         a.d_colors, a.d_opac, a.d_scales, a.d_rots, a.d_cov3d);
+}
+
+// register budget of project_bwd.  Since the parameter loads were hoisted above the SH wait (they overlap the
+// cp.async staging), 8 CTAs/SM (64 registers) spills: measured 0.147 ms vs 0.120 ms at 6 CTAs/SM (80 registers)
+// and 0.142 ms before the overlap.  B200GSR_PBWD_MINB = 8 | 6 | 5 selects for A/B runs.
+#ifndef GSR_PBWD_DEFAULT_MINB
+#define GSR_PBWD_DEFAULT_MINB 6
+#endif
+template <int MT>
+static void launch_project_bwd(const GsrBwdArgs& a, int g_begin, int g_end, size_t smem) {
+    static const int minb = [] { const char* e = getenv("B200GSR_PBWD_MINB"); return e ? atoi(e) : GSR_PBWD_DEFAULT_MINB; }();
+    if (minb == 8) launch_project_bwd_v<MT, 8>(a, g_begin, g_end, smem);
+    else if (minb == 5) launch_project_bwd_v<MT, 5>(a, g_begin, g_end, smem);
+    else launch_project_bwd_v<MT, 6>(a, g_begin, g_end, smem);
 }
 
 cudaError_t gsr_launch_project_bwd(const GsrBwdArgs& a) {

@@ -197,7 +197,6 @@ int b200gsr_backward_ex(const b200gsr_params* prm,
  * 16 rotations, 32 cov3D): set a bit when that destination is shared with an EARLIER view and the
  * view's contribution must be added instead of written (d_means2D is always per view).
  */
-#define B200GSR_MAX_VIEWS 16
 typedef struct b200gsr_view_inputs {
     const float *means3D, *shs, *colors_precomp, *opacities, *scales, *rotations, *cov3D_precomp;
 } b200gsr_view_inputs;
@@ -235,8 +234,13 @@ int b200gsr_mark_visible(int32_t P, const float* means3D, const float* viewmatri
  * the kernel from `seed` (counter-based Philox4x32-10; nothing is stored, backward regenerates).
  * Backward: d_* are the gradients w.r.t. the packed outputs, `grads` the per-group destinations
  * (same shapes as the raw parameters, fully overwritten).
+ * num_views = B > 1 (the views of one training step, each with its own augmentation): the raw parameters
+ * are read once; `scales` is [B,P,3] and `shs` [B,P,M,3] (z_scales [B,P,3], z_shs [B,P,M,3] or Philox
+ * streams per view), means3D / opacities / rotations are written once; the backward sums the per-view
+ * gradients of scales / shs in registers and writes every leaf gradient once.
  */
 #define B200GSR_MAX_GROUPS 24
+#define B200GSR_MAX_VIEWS 16
 typedef struct b200gsr_group {
     const float *xyz, *opacity, *scaling, *rotation, *f_dc, *f_rest;
     int32_t n;
@@ -244,12 +248,12 @@ typedef struct b200gsr_group {
 typedef struct b200gsr_group_grad {
     float *xyz, *opacity, *scaling, *rotation, *f_dc, *f_rest;
 } b200gsr_group_grad;
-int b200gsr_assemble_forward(int32_t num_groups, const b200gsr_group* groups, int32_t M,
+int b200gsr_assemble_forward(int32_t num_groups, const b200gsr_group* groups, int32_t M, int32_t num_views,
                              float shs_noise, float scale_noise, const float* z_shs, const float* z_scales,
                              uint64_t seed, float* means3D, float* opacities, float* scales, float* rotations,
                              float* shs, void* stream);
 int b200gsr_assemble_backward(int32_t num_groups, const b200gsr_group* groups, const b200gsr_group_grad* grads,
-                              int32_t M, float shs_noise, float scale_noise, const float* z_shs,
+                              int32_t M, int32_t num_views, float shs_noise, float scale_noise, const float* z_shs,
                               const float* z_scales, uint64_t seed, const float* d_means3D,
                               const float* d_opacities, const float* d_scales, const float* d_rotations,
                               const float* d_shs, void* stream);

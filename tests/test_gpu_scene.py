@@ -98,3 +98,39 @@ def test_assemble_feeds_the_rasterizer_end_to_end():
                                      scales=t["scales"], rotations=t["rotations"])
     assert torch.allclose(color, c2, atol=2e-5)
     assert all(torch.isfinite(v.grad).all() and float(v.grad.abs().max()) > 0 for h in halves for v in h.values())
+
+
+def test_assemble_multi_view_equals_per_view_calls():
+    """views=B: one pass over the raw parameters, B independently augmented copies of shs / scales; values and leaf
+    gradients equal B separate single-view calls with the same draws (torch noise) / are reproducible (Philox)."""
+    from dreamscene_b200.scene import assemble_scene
+    B, M = 3, 4
+    groups = _groups([700, 1300, 50], M, seed=9)
+    P = 2050
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    zs = torch.randn(B, P, M, 3, device="cuda", generator=gen)
+    zc = torch.randn(B, P, 3, device="cuda", generator=gen)
+    m, o, sc, r, sh = assemble_scene(groups, noise="torch", z_shs=zs, z_scales=zc, views=B)
+    assert sc.shape == (B, P, 3) and sh.shape == (B, P, M, 3)
+    w_sc, w_sh = torch.randn_like(sc), torch.randn_like(sh)
+    w_m, w_o, w_r = torch.randn_like(m), torch.randn_like(o), torch.randn_like(r)
+    torch.autograd.backward([m, o, sc, r, sh], [w_m, w_o, w_sc, w_r, w_sh])
+    got = [{k: v.grad.clone() for k, v in g.items()} for g in groups]
+    for g in groups:
+        for v in g.values():
+            v.grad = None
+    for v in range(B):
+        m1, o1, sc1, r1, sh1 = assemble_scene(groups, noise="torch", z_shs=zs[v], z_scales=zc[v])
+        assert torch.equal(sc1, sc[v]) and torch.equal(sh1, sh[v]) and torch.equal(m1, m) and torch.equal(r1, r)
+        torch.autograd.backward([m1, o1, sc1, r1, sh1],
+                                [w_m if v == 0 else torch.zeros_like(w_m), w_o if v == 0 else torch.zeros_like(w_o), w_sc[v],
+                                 w_r if v == 0 else torch.zeros_like(w_r), w_sh[v]])
+    for g, gg in zip(groups, got):
+        for k in g:
+            err = float((gg[k] - g[k].grad).abs().max() / g[k].grad.abs().max().clamp_min(1e-30))
+            assert err < 5e-6, (k, err)
+    a = assemble_scene(groups, noise="fused", seed=5, views=B)
+    b = assemble_scene(groups, noise="fused", seed=5, views=B)
+    assert torch.equal(a[4], b[4]) and not torch.equal(a[4][0], a[4][1])         # reproducible, views differ
+    single = assemble_scene(groups, noise="fused", seed=5)
+    assert torch.equal(single[4], a[4][0]) and torch.equal(single[2], a[2][0])    # view 0 == the single-view stream
