@@ -701,7 +701,7 @@ __device__ __forceinline__ void halve2(float (&v)[10], bool hi) {
 }
 
 
-template <int kSlots, int kMinCtas, int KFAST, bool STATS>
+template <int kSlots, int kMinCtas, int KFAST, bool STATS, bool PIPE = false>
 __global__ void __launch_bounds__(kWarps * 32, kMinCtas)
 composite_bwd2_kernel(int H, int W, int gx, int gy_view, int Hs, int ntiles, const uint32_t* __restrict__ header,
                       const uint32_t* __restrict__ work_order,
@@ -799,6 +799,75 @@ composite_bwd2_kernel(int H, int W, int gx, int gy_view, int Hs, int ntiles, con
             uint32_t mask = __ballot_sync(0xffffffffu, pass);
             const float4* sp = reinterpret_cast<const float4*>(st);
             const uint32_t pos0 = (uint32_t)(sidx * 32 + 1);
+#ifndef GSR_EXACT_EXP
+            if (PIPE) {
+                // Software-pipelined form of the loop below: the record loads and the exponent of the NEXT
+                // passing entry are issued before the current entry's body + butterfly run, so their LDS /
+                // MUFU latency hides behind ~100 independent instructions.  Decisions are unchanged.
+                struct Ev { float2 d; float A, Bq, Cq, op, depth, G, p2; const float4* rp; uint32_t pos; };
+                auto issue = [&](Ev& e) {
+                    const int b = 31 - __clz(mask);
+                    mask &= ~(1u << b);
+                    e.rp = sp + 3 * b;
+                    const float4 q0 = e.rp[0], q1 = e.rp[1];
+                    e.pos = pos0 + (uint32_t)b;
+                    e.d = __fadd2_rn(make_float2(q0.x, q0.y), XY);
+                    e.A = q0.w; e.Bq = q1.x; e.Cq = q1.y; e.op = q1.z; e.depth = q1.w;
+                    const float u = __fmaf_rn(e.A, e.d.x, __fmul_rn(e.Bq, e.d.y));
+                    e.p2 = __fmaf_rn(__fmul_rn(e.Cq, e.d.y), e.d.y, __fmul_rn(u, e.d.x));
+                    e.G = ex2_approx(e.p2);
+                };
+                Ev cur, nxt;
+                bool have = mask != 0u;
+                if (have) issue(cur);
+                while (have) {
+                    const bool have_next = mask != 0u;
+                    if (have_next) issue(nxt);
+                    const float alpha = fminf(GSR_ALPHA_MAX, __fmul_rn(cur.op, cur.G));
+                    const bool contrib = (cur.p2 <= 0.0f) && (alpha >= GSR_ALPHA_MIN) && cur.pos <= last;
+                    const uint32_t cm = __ballot_sync(0xffffffffu, contrib);
+                    if (cm != 0u) {
+                        const float4 q2 = cur.rp[2];
+                        const float2 d = cur.d;
+                        const float am = contrib ? alpha : 0.0f;
+                        const float Gm = contrib ? cur.G : 0.0f;
+                        const float rom = rcp_approx(1.0f - am);
+                        T = contrib ? T * rom : T;
+                        const float wgt = am * T;
+                        const float2 c01 = make_float2(q2.x, q2.y), c2D = make_float2(q2.z, cur.depth);
+                        const float2 d01 = __fadd2_rn(c01, make_float2(-acc01.x, -acc01.y));
+                        const float2 d2D = __fadd2_rn(c2D, make_float2(-acc2D.x, -acc2D.y));
+                        const float2 dot2 = __ffma2_rn(d2D, dC2D, __fmul2_rn(d01, dC01));
+                        const float dLda = (dot2.x + dot2.y) * T - bgT * rom;
+                        const float2 am2 = make_float2(am, am);
+                        acc01 = __ffma2_rn(am2, d01, acc01);
+                        acc2D = __ffma2_rn(am2, d2D, acc2D);
+                        float vv[10];
+                        vv[5] = Gm * dLda;
+                        const float gG = cur.op * vv[5];
+                        const float2 gs = __ffma2_rn(make_float2(cur.A + cur.A, cur.Cq + cur.Cq), d,
+                                                     __fmul2_rn(make_float2(cur.Bq, cur.Bq), make_float2(d.y, d.x)));
+                        const float2 gG2 = make_float2(gG, gG);
+                        const float2 v01 = __fmul2_rn(gG2, gs);
+                        const float2 tu = __fmul2_rn(gG2, d);
+                        const float2 v24 = __fmul2_rn(tu, d);
+                        vv[0] = v01.x; vv[1] = v01.y; vv[2] = v24.x; vv[3] = tu.x * d.y; vv[4] = v24.y;
+                        const float2 w2 = make_float2(wgt, wgt);
+                        const float2 v67 = __fmul2_rn(w2, dC01), v89 = __fmul2_rn(w2, dC2D);
+                        vv[6] = v67.x; vv[7] = v67.y; vv[8] = v89.x; vv[9] = v89.y;
+                        float* row = dgeom + 12 * (size_t)__float_as_uint(q2.w);
+                        halve2<10, 16>(vv, lane & 16);
+                        halve2<5, 8>(vv, lane & 8);
+                        halve2<3, 4>(vv, lane & 4);
+                        halve2<2, 2>(vv, lane & 2);
+                        const float tot = vv[0] + __shfl_xor_sync(0xffffffffu, vv[0], 1);
+                        if (commit_lane) atomicAdd(row + vidx, tot);
+                    }
+                    cur = nxt;
+                    have = have_next;
+                }
+            } else
+#endif
             while (mask) {
                 const int b = 31 - __clz(mask);
                 mask &= ~(1u << b);
@@ -995,14 +1064,14 @@ static cudaError_t launch_bwd(const GsrBwdArgs& a, const CompPtrs& c, uint32_t* 
     return cudaGetLastError();
 }
 
-template <int kSlots, int kMinCtas, int KFAST, bool STATS>
+template <int kSlots, int kMinCtas, int KFAST, bool STATS, bool PIPE = false>
 static cudaError_t launch_bwd2(const GsrBwdArgs& a, const CompPtrs& c, uint32_t* queue, float* dgeom) {
     const int smem = (int)sizeof(SmemRing<kSlots>);
     const int nblocks = min(c.grid.ntiles, a.num_sms * kMinCtas);
     static std::atomic<unsigned long long> attr_done{0};
-    cudaError_t e = gsr_smem_once(composite_bwd2_kernel<kSlots, kMinCtas, KFAST, STATS>, smem, attr_done);
+    cudaError_t e = gsr_smem_once(composite_bwd2_kernel<kSlots, kMinCtas, KFAST, STATS, PIPE>, smem, attr_done);
     if (e != cudaSuccess) return e;
-    composite_bwd2_kernel<kSlots, kMinCtas, KFAST, STATS><<<nblocks, kWarps * 32, smem, a.stream>>>(
+    composite_bwd2_kernel<kSlots, kMinCtas, KFAST, STATS, PIPE><<<nblocks, kWarps * 32, smem, a.stream>>>(
         a.prm.image_height, a.prm.image_width, c.grid.gx, a.gy_view, c.H, c.grid.ntiles, c.header, c.work_order, c.tile_start,
         c.keys, c.geom, a.prm.bg, queue, a.out_depth_alpha, c.n_contrib, a.dL_dcolor, a.dL_ddepth_alpha, dgeom,
         a.stats);
@@ -1025,6 +1094,8 @@ cudaError_t gsr_launch_composite_bwd(const GsrBwdArgs& a) {
         case 12: return launch_bwd2<3, 4, 2, false>(a, c, queue, dgeom);
         case 14: return launch_bwd2<3, 4, 4, false>(a, c, queue, dgeom);
         case 125: return launch_bwd2<3, 5, 2, false>(a, c, queue, dgeom);
+        case 20: return launch_bwd2<3, 4, 0, false, true>(a, c, queue, dgeom);     // software-pipelined body
+        case 23: return launch_bwd2<3, 3, 0, false, true>(a, c, queue, dgeom);     // ... with 85 registers, 3 CTAs/SM
         default: break;
     }
     static const int slots = [] { const char* e = getenv("B200GSR_BWD_SLOTS"); return e ? atoi(e) : 3; }();

@@ -2,6 +2,14 @@
 # GPU call 10: full suite on the final kernels, cfg5 in all modes, parity stats refresh, final bench + launch list
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/c10_pytest_all.log 2>&1; echo "rc=$?" >> gpurun_out/c10_pytest_all.log
+B200GSR_BWD_VARIANT=20 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_baseline_configs.py -m gpu -x -q -k "backward or cfg1 or sh_degrees or precomputed or zero_scales or screen_filling or odd_point or retain" > gpurun_out/c10_pytest_v20.log 2>&1; echo "rc=$?" >> gpurun_out/c10_pytest_v20.log
+for v in 10 20 23; do
+  B200GSR_BWD_VARIANT=$v timeout 300 python bench.py --steps 60 --warmup 20 --no-e2e --no-cpu-baseline > gpurun_out/c10_bench_v$v.json 2> gpurun_out/c10_bench_v$v.err
+  python -c "
+import json
+b=json.loads(open('gpurun_out/c10_bench_v$v.json').read().strip().splitlines()[-1]); print('v$v', round(b['ms_per_step'],4), b['stages_ms']['composite_bwd'])"
+done
+tail -2 gpurun_out/c10_pytest_v20.log
 for g in torch fused_rng views; do
   timeout 300 python benchmarks/scene_step.py --steps 15 --warmup 5 --glue $g > gpurun_out/c10_scene_$g.json 2> gpurun_out/c10_scene_$g.err
 done
