@@ -122,8 +122,10 @@ struct __align__(128) SmemCta {
     uint32_t work;           // broadcast slot for the tile queue
 };
 
-template <bool SCORE, int PPL, bool STATS>
-__global__ void __launch_bounds__(256 / PPL)
+// PARTS = 1: one CTA of 8 warps per tile.  PARTS = 2 (A/B variant): a tile is rendered by two CTAs of 4 warps,
+// each taking an 16x8 half (both gather the whole list; fewer warps per barrier, twice as many barrier groups).
+template <bool SCORE, int PPL, bool STATS, int PARTS = 1>
+__global__ void __launch_bounds__(256 / PPL / PARTS)
 composite_fwd_kernel(int H, int W, int gx, int gy_view, int Hs, int ntiles, const uint32_t* __restrict__ header,
                      const uint32_t* __restrict__ work_order,
                      const uint32_t* __restrict__ tile_start,
@@ -132,7 +134,7 @@ composite_fwd_kernel(int H, int W, int gx, int gy_view, int Hs, int ntiles, cons
                      float* __restrict__ out_color, float* __restrict__ out_depth_alpha,
                      uint32_t* __restrict__ n_contrib, float* __restrict__ score,
                      unsigned long long* __restrict__ stats) {
-    constexpr int kThreads = 256 / PPL;
+    constexpr int kThreads = 256 / PPL / PARTS;
     unsigned int st_eval = 0, st_lanes = 0;
     constexpr int kPer = kChunk / kThreads;   // list entries gathered per thread per chunk
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -147,8 +149,9 @@ composite_fwd_kernel(int H, int W, int gx, int gy_view, int Hs, int ntiles, cons
         __syncthreads();
         const uint32_t w = sm.work;
         __syncthreads();   // everyone has read the slot before thread 0 may overwrite it
-        if (w >= (uint32_t)ntiles) break;
-        const uint32_t tile = work_order[w];
+        if (w >= (uint32_t)ntiles * PARTS) break;
+        const uint32_t tile = work_order[w / PARTS];
+        const int blk = (int)(w % PARTS) * (kThreads / 32) + wid;      // 8x(4*PPL)-pixel block of the tile this warp renders
         uint32_t beg = tile_start[tile], end = tile_start[tile + 1];
         if (end > max_pairs) end = max_pairs;
         if (beg > end) beg = end;
@@ -162,7 +165,7 @@ composite_fwd_kernel(int H, int W, int gx, int gy_view, int Hs, int ntiles, cons
         const int row0 = view * gy_view * GSR_TILE;
         const float* bgv = bg + 3 * view;
         const float bg0 = __ldg(bgv), bg1 = __ldg(bgv + 1), bg2 = __ldg(bgv + 2);
-        const int X0i = txi * GSR_TILE + (wid & 1) * 8, Y0i = tyi * GSR_TILE + (wid >> 1) * (4 * PPL);
+        const int X0i = txi * GSR_TILE + (blk & 1) * 8, Y0i = tyi * GSR_TILE + (blk >> 1) * (4 * PPL);
         const int Xi = X0i + (lane & 7), Yi = Y0i + (lane >> 3);
         const float X0 = (float)X0i, Y0 = (float)Y0i, X = (float)Xi;
         bool inside[PPL], done[PPL];
@@ -1042,6 +1045,17 @@ cudaError_t gsr_launch_composite_fwd(const GsrFwdArgs& a) {
     const int nblocks = min(c.grid.ntiles, a.num_sms * 6);
     // B200GSR_FWD_VARIANT = 1 | 2: bulk-copy / TMA staging experiments (profiles/r02_tma_ab.md)
     static const int fwd_variant = [] { const char* e = getenv("B200GSR_FWD_VARIANT"); return e ? atoi(e) : 0; }();
+    if (fwd_variant == 4 && !a.prm.score_flag && a.stats == nullptr) {     // two 4-warp CTAs per tile
+        const int smem = (int)sizeof(SmemCta);
+        static std::atomic<unsigned long long> attr_done4{0};
+        cudaError_t e4 = gsr_smem_once(composite_fwd_kernel<false, 1, false, 2>, smem, attr_done4);
+        if (e4 != cudaSuccess) return e4;
+        const int nb4 = min(2 * c.grid.ntiles, a.num_sms * 8);
+        composite_fwd_kernel<false, 1, false, 2><<<nb4, 128, smem, a.stream>>>(
+            a.prm.image_height, a.prm.image_width, c.grid.gx, a.gy_view, c.H, c.grid.ntiles, c.header, c.work_order, c.tile_start,
+            c.keys, c.geom, a.prm.bg, queue, a.out_color, a.out_depth_alpha, c.n_contrib, a.score, a.stats);
+        return cudaGetLastError();
+    }
     if (fwd_variant != 0 && !a.prm.score_flag && a.stats == nullptr && a.num_views == 1) {
         const int nb = min(c.grid.ntiles, a.num_sms * 5);
         return fwd_variant == 2 ? launch_fwd_tma<2>(a, nb, c, queue) : launch_fwd_tma<1>(a, nb, c, queue);

@@ -167,8 +167,12 @@ def _resolve_pending(d: _Device, block: bool = False) -> None:
 
 def flush_checks(device=None) -> None:
     """Wait for every forward issued so far to report its pair count (raises on overflow)."""
-    for d in list(_devices.values()):
-        if device is None or d.device == torch.device(device):
+    want = None
+    if device is not None:
+        dv = torch.device(device)
+        want = dv.index if dv.index is not None else torch.cuda.current_device()
+    for idx, d in list(_devices.items()):
+        if want is None or idx == want:
             _resolve_pending(d, block=True)
 
 
@@ -213,7 +217,7 @@ def _make_params(rs: GaussianRasterizationSettings, P: int, M: int, keep: list, 
 
 class _State:
     """Everything backward needs that is not a tensor input."""
-    __slots__ = ("params_keep", "P", "M", "capacity", "saved", "rs", "with_backward")
+    __slots__ = ("params_keep", "P", "M", "capacity", "saved", "rs", "with_backward", "prm")
 
 
 _layout_cache: dict = {}
@@ -329,6 +333,7 @@ def _forward_impl(rs, means3D, shs, colors, opac, scales, rots, cov3d, with_back
     st = _State()
     st.params_keep = keep; st.P = P; st.M = M; st.capacity = cap; st.saved = saved; st.rs = rs
     st.with_backward = with_backward
+    st.prm = prm                      # the backward reuses the struct (its device pointers are kept alive by `keep`)
     return color, radii, depth_alpha, score, st
 
 
@@ -421,9 +426,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                 raise RuntimeError("b200gsr: backward through a forward that ran without gradient accumulators")
             if not torch.cuda.is_current_stream_capturing():
                 _resolve_pending(_device_state(dev))      # non-blocking overflow check of earlier forwards
-            keep: list = []
             with torch.cuda.device(dev):
-                prm = _make_params(rs, P, M, keep, dev)
+                prm = st.prm
                 stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
                 def launch(stages, g0, g1):
