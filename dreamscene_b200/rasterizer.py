@@ -61,8 +61,9 @@ class PairCapacityOverflow(RuntimeError):
 class _Device:
     def __init__(self, device: torch.device):
         self.device = device
-        self.capacity = 0            # pair capacity used for the next call (only ever grows for a given shape)
-        self.cap_key = None          # (P, H, W) the capacity was measured for: a new shape is re-measured
+        self.capacity = 0            # largest pair capacity in use (fallback inside CUDA-graph capture)
+        self.caps: dict = {}         # shape key (P, H, W) / (B, P, H, W) -> measured capacity (only ever grows);
+                                     # a shape seen for the first time is measured synchronously
         self.user_capacity = False   # set by set_workspace_capacity: trust it, never wait on it
         self.last_pairs = 0          # pair count of the most recent RESOLVED forward
         self.seq = 0
@@ -142,19 +143,21 @@ def _resolve_pending(d: _Device, block: bool = False) -> None:
     n = d.notify_np
     still, overflow = [], None
     t0 = time.perf_counter()
-    for slot, seq, cap in d.pending:
+    for slot, seq, cap, key in d.pending:
         while block and int(n[slot, 0]) != seq:
             if time.perf_counter() - t0 > _POLL_TIMEOUT_S:
                 torch.cuda.synchronize(d.device)
                 if int(n[slot, 0]) != seq:
                     raise RuntimeError("b200gsr: device never reported a pair count")
         if int(n[slot, 0]) != seq:
-            still.append((slot, seq, cap))
+            still.append((slot, seq, cap, key))
             continue
         pairs = int(n[slot, 1]) & 0xFFFFFFFF
         d.free_slots.append(slot)
         d.last_pairs = pairs
         d.capacity = max(d.capacity, _round_cap(2 * pairs))
+        if key is not None and not d.user_capacity:
+            d.caps[key] = max(d.caps.get(key, 0), _round_cap(2 * pairs))
         if pairs > cap:
             overflow = (pairs, cap)
     d.pending = still
@@ -241,13 +244,14 @@ def _issue_with_capacity(d: _Device, dev, key, P_eff: int, H_eff: int, W: int, w
     capacity) and re-issues on overflow.  -> (saved tensor, capacity)."""
     capturing = torch.cuda.is_current_stream_capturing()
     stream_h = torch.cuda.current_stream(dev).cuda_stream
-    known = d.capacity > 0 and (d.user_capacity or d.cap_key == key)
-    if capturing and d.capacity > 0:
-        known = True                   # cannot wait inside a capture: trust the high-water mark
+    measured = d.capacity if d.user_capacity else d.caps.get(key, 0)
+    known = measured > 0
+    if capturing and not known and d.capacity > 0:
+        known, measured = True, d.capacity      # cannot wait inside a capture: trust the device's high-water mark
     if capturing and not known:
         raise RuntimeError("b200gsr: capturing into a CUDA graph needs a known pair capacity: run one eager "
                            "forward on this device first or call set_workspace_capacity()")
-    cap = _round_cap(max(d.capacity, _MIN_PAIRS_PER_GAUSSIAN * P_eff)) if known else _round_cap(6 * P_eff)
+    cap = _round_cap(max(measured, _MIN_PAIRS_PER_GAUSSIAN * P_eff)) if known else _round_cap(6 * P_eff)
     # wait for the count only when it is needed: sync mode, or the capacity is a blind first guess
     wait = (not capturing) and (_pair_mode == "sync" or not known)
     while True:
@@ -271,7 +275,7 @@ def _issue_with_capacity(d: _Device, dev, key, P_eff: int, H_eff: int, W: int, w
         if capturing:
             break
         if not wait:
-            d.pending.append((slot, seq, cap))       # resolved lazily, never blocks the host
+            d.pending.append((slot, seq, cap, key))  # resolved lazily, never blocks the host
             break
         # Wait only for the tile scan (project + count + scan kernels); sort/composite keep running.
         t0 = time.perf_counter()
@@ -290,11 +294,14 @@ def _issue_with_capacity(d: _Device, dev, key, P_eff: int, H_eff: int, W: int, w
             # views of one training step differ a lot in pair count (random cameras).  A new
             # shape starts its own high-water mark.
             if not d.user_capacity:
-                fresh = d.cap_key != key
-                d.capacity = _round_cap(2 * pairs) if fresh else max(d.capacity, _round_cap(2 * pairs))
-                d.cap_key = key
+                d.caps[key] = max(d.caps.get(key, 0), _round_cap(2 * pairs))
+                d.capacity = max(d.capacity, d.caps[key])
+                if len(d.caps) > 64:                 # densification changes P every 100 steps: keep the table small
+                    for k in list(d.caps)[:-32]:
+                        del d.caps[k]
             break
-        cap = d.capacity = _round_cap(2 * pairs)   # overflow: re-issue with enough room
+        cap = _round_cap(2 * pairs)                  # overflow: re-issue with enough room
+        d.capacity = max(d.capacity, cap)
         if score is not None:
             score.zero_()
     return saved, cap

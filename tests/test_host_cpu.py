@@ -117,13 +117,13 @@ def test_deferred_overflow_check_reads_the_notify_ring_without_blocking():
     d.notify_np = d.notify.numpy()
     d.free_slots = list(range(R._NOTIFY_SLOTS - 1, -1, -1))
     s1, s2 = d.free_slots.pop(), d.free_slots.pop()
-    d.pending = [(s1, 11, 1 << 20), (s2, 12, 1 << 20)]
+    d.pending = [(s1, 11, 1 << 20, (5, 16, 16)), (s2, 12, 1 << 20, (5, 16, 16))]
     R._resolve_pending(d)                       # nothing reported yet: stays pending, no wait
     assert len(d.pending) == 2
     d.notify_np[s1] = (11, 500_000, 0, 64)      # first forward reports 0.5M pairs
     R._resolve_pending(d)
-    assert d.pending == [(s2, 12, 1 << 20)] and d.last_pairs == 500_000 and s1 in d.free_slots
-    assert d.capacity == R._round_cap(1_000_000)
+    assert d.pending == [(s2, 12, 1 << 20, (5, 16, 16))] and d.last_pairs == 500_000 and s1 in d.free_slots
+    assert d.capacity == R._round_cap(1_000_000) and d.caps[(5, 16, 16)] == R._round_cap(1_000_000)
     d.notify_np[s2] = (12, 3 << 20, 1, 64)      # second one overflowed its 1M-pair buffer
     with pytest.raises(R.PairCapacityOverflow):
         R._resolve_pending(d)
