@@ -156,7 +156,7 @@ int b200gsr_scratch_layout_query(int32_t P, int32_t H, int32_t W, uint64_t max_p
     out->tile_cursor = off; off = align_up(off + (size_t)GSR_COPIES * g.ntiles * sizeof(uint32_t));
     out->rectdepth = off;   off = align_up(off + (size_t)P * sizeof(uint4));
     {
-        const size_t nblk = ((size_t)P + 1024 * GSR_MS_ITEMS - 1) / (1024 * GSR_MS_ITEMS);
+        const size_t nblk = (size_t)gsr_ms_blocks(P);
         out->ms_hist = off; off = align_up(off + (gsr_use_multisplit(g.ntiles) ? nblk * g.ntiles * sizeof(uint32_t) : 0));
     }
     out->total = off;

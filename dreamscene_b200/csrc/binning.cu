@@ -260,19 +260,19 @@ scatter_kernel(int P, int gx, int ntiles, uint32_t max_pairs, const uint4* __res
 // ---------------------------------------------------------------------------------------------
 template <bool SCATTER>
 __global__ void __launch_bounds__(1024)
-multisplit_kernel(int P, int gx, int ntiles, uint32_t max_pairs, const uint4* __restrict__ rectdepth,
+multisplit_kernel(int P, int per, int gx, int ntiles, uint32_t max_pairs, const uint4* __restrict__ rectdepth,
                   uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_cursor,
                   uint32_t* __restrict__ block_hist, unsigned long long* __restrict__ keys) {
     extern __shared__ uint32_t ms_smem[];
-    uint32_t* hist = ms_smem;            // [ntiles] counts, later in-slice cursors
-    uint32_t* base = ms_smem + ntiles;   // [ntiles] start of this CTA's slice (SCATTER only)
-    const int i0 = blockIdx.x * (1024 * GSR_MS_ITEMS);
+    uint32_t* hist = ms_smem;            // [ntiles] counts (count) / global write cursors of this CTA's slices (scatter)
+    const int i0 = blockIdx.x * per;                 // this CTA's Gaussians: [i0, min(P, i0 + per)), per <= 4096
+    const int i1 = min(P, i0 + per);
     uint32_t* my_hist = block_hist + (size_t)blockIdx.x * ntiles;   // written by count, re-read by scatter
     uint4 rd[GSR_MS_ITEMS];
 #pragma unroll
     for (int u = 0; u < GSR_MS_ITEMS; ++u) {
         const int i = i0 + u * 1024 + threadIdx.x;
-        rd[u] = (i < P) ? __ldg(rectdepth + i) : make_uint4(0u, 0u, 0u, 0u);
+        rd[u] = (i < i1) ? __ldg(rectdepth + i) : make_uint4(0u, 0u, 0u, 0u);
     }
     if constexpr (!SCATTER) {
         for (int t = threadIdx.x; t < ntiles; t += 1024) hist[t] = 0u;
@@ -292,11 +292,11 @@ multisplit_kernel(int P, int gx, int ntiles, uint32_t max_pairs, const uint4* __
             if (c) atomicAdd(tile_count + t, c);
         }
     } else {
-        // reserve this CTA's slice of every touched tile, zero the in-slice cursors
+        // reserve this CTA's slice of every touched tile: the in-slice cursor starts at the slice's
+        // global position, so a pair's slot is ONE shared-memory atomic (no second lookup)
         for (int t = threadIdx.x; t < ntiles; t += 1024) {
             const uint32_t c = my_hist[t];
-            hist[t] = 0u;
-            if (c) base[t] = atomicAdd(tile_cursor + t, c);
+            if (c) hist[t] = atomicAdd(tile_cursor + t, c);
         }
         __syncthreads();
 #pragma unroll
@@ -307,8 +307,7 @@ multisplit_kernel(int P, int gx, int ntiles, uint32_t max_pairs, const uint4* __
                 const unsigned long long key = ((unsigned long long)rd[u].z << 32) | (uint32_t)i;
                 for (int ty = miny; ty < maxy; ++ty)
                     for (int tx = minx; tx < maxx; ++tx) {
-                        const int t = ty * gx + tx;
-                        const uint32_t pos = base[t] + atomicAdd(&hist[t], 1u);
+                        const uint32_t pos = atomicAdd(&hist[ty * gx + tx], 1u);
                         if (pos < max_pairs) keys[pos] = key;
                     }
             }
@@ -445,29 +444,37 @@ __device__ __forceinline__ void radix_sort_smem(unsigned long long* s, uint32_t*
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fast path: one-pass interpolation bucket sort.  Depth bits are mapped monotonically onto NB
-// buckets between the list's min and max; a shared-memory atomic hands every key its slot inside
-// the bucket; then one thread insertion-sorts each (tiny) bucket on the FULL 64-bit key, which
-// also orders equal depths by index.  If any bucket is larger than kBucketLimit (skewed depth
-// distribution) the list falls back to the radix sort above.  Returns with s[0..n) sorted.
+// Fast path: one-pass interpolation bucket sort.  The keys are read from global memory straight into
+// registers (g[0..n), coalesced); depth bits are mapped monotonically onto NB buckets between the
+// list's min and max; a shared-memory atomic hands every key its arrival slot inside the bucket and
+// the keys are scattered bucket by bucket into s.  Every key then counts the smaller FULL 64-bit
+// keys of its own (tiny) bucket - one thread per key, no dependent read-modify-write chains - which
+// is its final position (keys are distinct: the low word is the Gaussian index), and is written
+// there.  If any bucket is larger than kBucketLimit (skewed depth distribution) the list falls back
+// to the radix sort above.  Returns with s[0..n) sorted; the caller copies it out.
 // ---------------------------------------------------------------------------------------------
 constexpr int kBucketLimit = 32;
 
 template <int NT, int ITEMS, int NB>
-__device__ __forceinline__ void tile_sort_smem(unsigned long long* s, uint32_t* hist, uint32_t* digit_base,
-                                               uint32_t* red, int n) {
-    static_assert(NB <= (NT / 32) * 256, "bucket counters alias the radix histogram");
+__device__ __forceinline__ void tile_sort_smem(const unsigned long long* g, unsigned long long* s, uint32_t* hist,
+                                               uint32_t* digit_base, uint32_t* red, int n) {
+    static_assert(NB + 1 <= (NT / 32) * 256 + 32, "bucket counters alias the radix histogram (+32 spare words)");
     static_assert(NB % NT == 0, "whole number of buckets per thread");
+    static_assert(NT / 32 <= 32 && ITEMS % 2 == 0, "one lane per warp total; positions are packed in pairs");
     constexpr int BPT = NB / NT;
     const int tid = threadIdx.x, lane = tid & 31;
-    uint32_t* cnt = hist;   // NB counters, later exclusive starts
+    uint32_t* cnt = hist;   // NB counters, later NB + 1 exclusive starts
+    const int rows = (n + NT - 1) / NT;       // items per thread actually in use (CTA-uniform): rows past it are skipped
     unsigned long long k[ITEMS];
     uint32_t dmin = 0xffffffffu, dmax = 0u;
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         const int e = j * NT + tid;
-        k[j] = e < n ? s[e] : ~0ull;
-        if (e < n) { dmin = min(dmin, (uint32_t)(k[j] >> 32)); dmax = max(dmax, (uint32_t)(k[j] >> 32)); }
+        k[j] = ~0ull;
+        if (j < rows && e < n) {
+            k[j] = __ldcg(g + e);                 // L2: the multi-chunk caller rewrites g between calls
+            dmin = min(dmin, (uint32_t)(k[j] >> 32)); dmax = max(dmax, (uint32_t)(k[j] >> 32));
+        }
     }
     dmin = __reduce_min_sync(0xffffffffu, dmin);
     dmax = __reduce_max_sync(0xffffffffu, dmax);
@@ -479,16 +486,16 @@ __device__ __forceinline__ void tile_sort_smem(unsigned long long* s, uint32_t* 
     __syncthreads();
     dmin = red[0]; dmax = red[1];
     const float scale = (float)NB / ((float)(dmax - dmin) + 1.0f);
-    uint32_t rank8[(ITEMS + 3) / 4];   // rank inside the bucket, one byte per item (saturating)
+    auto bucket_of = [&](unsigned long long key) {
+        return min((uint32_t)(NB - 1), (uint32_t)((float)((uint32_t)(key >> 32) - dmin) * scale));
+    };
+    uint32_t rank8[(ITEMS + 3) / 4];   // arrival rank inside the bucket, one byte per item (saturating)
 #pragma unroll
     for (int j = 0; j < (ITEMS + 3) / 4; ++j) rank8[j] = 0u;
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         const int e = j * NT + tid;
-        if (e < n) {
-            const uint32_t b = min((uint32_t)(NB - 1), (uint32_t)((float)((uint32_t)(k[j] >> 32) - dmin) * scale));
-            rank8[j >> 2] |= min(atomicAdd(&cnt[b], 1u), 255u) << (8 * (j & 3));
-        }
+        if (j < rows && e < n) rank8[j >> 2] |= min(atomicAdd(&cnt[bucket_of(k[j])], 1u), 255u) << (8 * (j & 3));
     }
     __syncthreads();
     // exclusive scan of the NB counters (BPT consecutive counters per thread) + largest bucket
@@ -505,7 +512,12 @@ __device__ __forceinline__ void tile_sort_smem(unsigned long long* s, uint32_t* 
     if (lane == 31) digit_base[tid >> 5] = incl;
     if (lane == 0 && big > (uint32_t)kBucketLimit) red[2] = 1u;
     __syncthreads();
-    if (red[2] != 0u) {   // skewed list (uniform branch): robust path; s still holds the input
+    if (red[2] != 0u) {   // skewed list (uniform branch): robust path, which sorts s in place
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const int e = j * NT + tid;
+            if (j < rows && e < n) s[e] = k[j];
+        }
         __syncthreads();
         radix_sort_smem<NT, ITEMS>(s, hist, digit_base, red, n, false);
         if (red[0] != 0u) {   // long runs of equal depth: sort again on all 64 bits
@@ -514,31 +526,49 @@ __device__ __forceinline__ void tile_sort_smem(unsigned long long* s, uint32_t* 
         }
         return;
     }
-    uint32_t wbase = 0;
-    for (int ww = 0; ww < (tid >> 5); ++ww) wbase += digit_base[ww];
-    uint32_t run = wbase + incl - sum;
-    uint32_t start[BPT];
+    // warps before mine: one lane per warp total, summed with a warp reduction
+    const uint32_t wt = (lane < NT / 32 && lane < (tid >> 5)) ? digit_base[lane] : 0u;
+    uint32_t run = __reduce_add_sync(0xffffffffu, wt) + incl - sum;
 #pragma unroll
-    for (int q = 0; q < BPT; ++q) { start[q] = run; cnt[tid * BPT + q] = run; run += c[q]; }
+    for (int q = 0; q < BPT; ++q) { cnt[tid * BPT + q] = run; run += c[q]; }
+    if (tid == NT - 1) cnt[NB] = (uint32_t)n;
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         const int e = j * NT + tid;
-        if (e < n) {
-            const uint32_t b = min((uint32_t)(NB - 1), (uint32_t)((float)((uint32_t)(k[j] >> 32) - dmin) * scale));
-            s[cnt[b] + ((rank8[j >> 2] >> (8 * (j & 3))) & 0xffu)] = k[j];
+        if (j < rows && e < n) s[cnt[bucket_of(k[j])] + ((rank8[j >> 2] >> (8 * (j & 3))) & 0xffu)] = k[j];
+    }
+    __syncthreads();
+    // s is now ordered bucket by bucket.  Each thread takes the keys at ITS positions (the registers'
+    // original keys are dead): the lanes of a warp then sit in the same few neighbouring buckets, so
+    // their counting loops have near-equal length and read the same addresses (broadcasts).
+    uint32_t pos2[ITEMS / 2];          // final positions (< 65536), two per register
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const int e = j * NT + tid;
+        uint32_t pos = 0u;
+        if (j < rows && e < n) {
+            const unsigned long long x = s[e];
+            k[j] = x;
+            const uint32_t b = bucket_of(x);
+            const uint32_t b0 = cnt[b], b1 = cnt[b + 1];
+            pos = b0;
+            uint32_t a = b0;
+#pragma unroll 1
+            for (; a + 2 <= b1; a += 2) {              // two independent loads per trip (buckets hold ~1-3 keys)
+                const unsigned long long y0 = s[a], y1 = s[a + 1];
+                pos += (y0 < x) ? 1u : 0u;
+                pos += (y1 < x) ? 1u : 0u;
+            }
+            if (a < b1) pos += (s[a] < x) ? 1u : 0u;
         }
+        if (j & 1) pos2[j >> 1] |= pos << 16; else pos2[j >> 1] = pos;
     }
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < BPT; ++q) {
-        const int b0 = (int)start[q], m = (int)c[q];
-        for (int a = b0 + 1; a < b0 + m; ++a) {
-            const unsigned long long x = s[a];
-            int b = a - 1;
-            while (b >= b0 && s[b] > x) { s[b + 1] = s[b]; --b; }
-            s[b + 1] = x;
-        }
+    for (int j = 0; j < ITEMS; ++j) {
+        const int e = j * NT + tid;
+        if (j < rows && e < n) s[(pos2[j >> 1] >> (16 * (j & 1))) & 0xffffu] = k[j];
     }
     __syncthreads();
 }
@@ -549,13 +579,13 @@ __device__ __forceinline__ int next_pow2(int n) {
 
 struct SortSmemSmall {
     unsigned long long keys[GSR_SORT_SMALL_MAX];
-    uint32_t hist[8 * 256];
+    uint32_t hist[8 * 256 + 32];
     uint32_t digit_base[256 + 8];
     uint32_t red[4];
 };
 struct SortSmemBig {
     unsigned long long keys[GSR_SORT_BIG_CHUNK];
-    uint32_t hist[32 * 256];
+    uint32_t hist[32 * 256 + 32];
     uint32_t digit_base[256 + 8];
     uint32_t red[4];
 };
@@ -575,9 +605,7 @@ sort_small_kernel(const uint32_t* __restrict__ header, const uint32_t* __restric
         if (end > max_pairs) end = max_pairs;                  // overflow: stay in bounds
         if (beg >= end) continue;
         const int n = (int)(end - beg);
-        for (int i = threadIdx.x; i < n; i += 256) sm.keys[i] = keys[beg + i];
-        __syncthreads();
-        tile_sort_smem<256, 16, 1024>(sm.keys, sm.hist, sm.digit_base, sm.red, n);
+        tile_sort_smem<256, 16, 2048>(keys + beg, sm.keys, sm.hist, sm.digit_base, sm.red, n);
         for (int i = threadIdx.x; i < n; i += 256) keys[beg + i] = sm.keys[i];
         __syncthreads();
     }
@@ -603,9 +631,7 @@ sort_big_kernel(const uint32_t* __restrict__ header, const uint32_t* __restrict_
         const int n = (int)(end - beg);
         unsigned long long* gk = keys + beg;
         if (n <= CH) {
-            for (int i = threadIdx.x; i < n; i += 1024) sb[i] = gk[i];
-            __syncthreads();
-            tile_sort_smem<1024, 16, 4096>(sb, sm.hist, sm.digit_base, sm.red, n);
+            tile_sort_smem<1024, 16, 8192>(gk, sb, sm.hist, sm.digit_base, sm.red, n);
             for (int i = threadIdx.x; i < n; i += 1024) gk[i] = sb[i];
             __syncthreads();
             continue;
@@ -614,9 +640,7 @@ sort_big_kernel(const uint32_t* __restrict__ header, const uint32_t* __restrict_
         const int N = next_pow2(n);
         for (int c0 = 0; c0 < n; c0 += CH) {
             const int m = min(CH, n - c0);
-            for (int i = threadIdx.x; i < m; i += 1024) sb[i] = __ldcg(gk + c0 + i);
-            __syncthreads();
-            tile_sort_smem<1024, 16, 4096>(sb, sm.hist, sm.digit_base, sm.red, m);
+            tile_sort_smem<1024, 16, 8192>(gk + c0, sb, sm.hist, sm.digit_base, sm.red, m);
             for (int i = threadIdx.x; i < m; i += 1024) __stcg(gk + c0 + i, sb[i]);
             __syncthreads();
         }
@@ -710,20 +734,21 @@ cudaError_t gsr_launch_scan(const GsrFwdArgs& a) {
 static cudaError_t launch_multisplit(const GsrFwdArgs& a, const BinPtrs& b, bool scatter) {
     const int P = a.num_views * a.P_view;     // virtual Gaussians (view-major)
     if (P == 0) return cudaSuccess;
-    const int per = 1024 * GSR_MS_ITEMS;
-    const int smem = 2 * b.grid.ntiles * (int)sizeof(uint32_t);
-    const int smem_max = 2 * GSR_MS_MAX_TILES * (int)sizeof(uint32_t);
+    const int nblk = gsr_ms_blocks(P);
+    const int per = (P + nblk - 1) / nblk;
+    const int smem = b.grid.ntiles * (int)sizeof(uint32_t);
+    const int smem_max = GSR_MS_MAX_TILES * (int)sizeof(uint32_t);
     static std::atomic<unsigned long long> done_scatter{0}, done_count{0};
     cudaError_t e = scatter ? gsr_smem_once(multisplit_kernel<true>, smem_max, done_scatter)
                             : gsr_smem_once(multisplit_kernel<false>, smem_max, done_count);
     if (e != cudaSuccess) return e;
     if (scatter)
-        multisplit_kernel<true><<<(P + per - 1) / per, 1024, smem, a.stream>>>(
-            P, b.grid.gx, b.grid.ntiles, a.max_pairs, b.rectdepth, b.tile_count, b.tile_cursor,
+        multisplit_kernel<true><<<nblk, 1024, smem, a.stream>>>(
+            P, per, b.grid.gx, b.grid.ntiles, a.max_pairs, b.rectdepth, b.tile_count, b.tile_cursor,
             reinterpret_cast<uint32_t*>(a.scratch + a.sl.ms_hist), b.keys);
     else
-        multisplit_kernel<false><<<(P + per - 1) / per, 1024, smem, a.stream>>>(
-            P, b.grid.gx, b.grid.ntiles, a.max_pairs, b.rectdepth, b.tile_count, b.tile_cursor,
+        multisplit_kernel<false><<<nblk, 1024, smem, a.stream>>>(
+            P, per, b.grid.gx, b.grid.ntiles, a.max_pairs, b.rectdepth, b.tile_count, b.tile_cursor,
             reinterpret_cast<uint32_t*>(a.scratch + a.sl.ms_hist), b.keys);
     return cudaGetLastError();
 }

@@ -69,7 +69,17 @@ enum { GSR_C_FWD_QUEUE = 0 };
 // threads owns GSR_MS_ITEMS*1024 consecutive Gaussians and histograms their tile hits in smem, so
 // global atomics drop from one per (Gaussian, tile) pair to one per (CTA, touched tile).
 #define GSR_MS_ITEMS 4
-#define GSR_MS_MAX_TILES 12288   // 2 x 4 B x tiles of dynamic smem (96 KB)
+// Number of multisplit CTAs for P (virtual) Gaussians: at most 4096 Gaussians per CTA; a scene that
+// would fill less than one wave (2 CTAs x 148 SMs) is spread over the whole wave instead, down to 256
+// Gaussians per CTA, so that every SM carries the same load.
+#define GSR_MS_WAVE_CTAS 296
+__host__ __device__ inline int gsr_ms_blocks(long long P) {
+    const long long full = (P + 1024 * GSR_MS_ITEMS - 1) / (1024 * GSR_MS_ITEMS);
+    if (full >= GSR_MS_WAVE_CTAS) return (int)full;
+    const long long fine = (P + 255) / 256;
+    return (int)(fine < 1 ? 1 : (fine < GSR_MS_WAVE_CTAS ? fine : GSR_MS_WAVE_CTAS));
+}
+#define GSR_MS_MAX_TILES 12288   // 4 B x tiles of dynamic smem (48 KB); 12 tiles per thread in the scan kernel
 __host__ __device__ inline bool gsr_use_multisplit(int ntiles) { return ntiles <= GSR_MS_MAX_TILES; }
 
 #ifdef __CUDACC__
