@@ -456,7 +456,7 @@ __device__ __forceinline__ void radix_sort_smem(unsigned long long* s, uint32_t*
 constexpr int kBucketLimit = 32;
 
 template <int NT, int ITEMS, int NB>
-__device__ __forceinline__ void tile_sort_smem(const unsigned long long* g, unsigned long long* s, uint32_t* hist,
+__device__ __forceinline__ void tile_sort_items(const unsigned long long* g, unsigned long long* s, uint32_t* hist,
                                                uint32_t* digit_base, uint32_t* red, int n) {
     static_assert(NB + 1 <= (NT / 32) * 256 + 32, "bucket counters alias the radix histogram (+32 spare words)");
     static_assert(NB % NT == 0, "whole number of buckets per thread");
@@ -464,14 +464,13 @@ __device__ __forceinline__ void tile_sort_smem(const unsigned long long* g, unsi
     constexpr int BPT = NB / NT;
     const int tid = threadIdx.x, lane = tid & 31;
     uint32_t* cnt = hist;   // NB counters, later NB + 1 exclusive starts
-    const int rows = (n + NT - 1) / NT;       // items per thread actually in use (CTA-uniform): rows past it are skipped
     unsigned long long k[ITEMS];
     uint32_t dmin = 0xffffffffu, dmax = 0u;
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         const int e = j * NT + tid;
         k[j] = ~0ull;
-        if (j < rows && e < n) {
+        if (e < n) {
             k[j] = __ldcg(g + e);                 // L2: the multi-chunk caller rewrites g between calls
             dmin = min(dmin, (uint32_t)(k[j] >> 32)); dmax = max(dmax, (uint32_t)(k[j] >> 32));
         }
@@ -495,7 +494,7 @@ __device__ __forceinline__ void tile_sort_smem(const unsigned long long* g, unsi
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         const int e = j * NT + tid;
-        if (j < rows && e < n) rank8[j >> 2] |= min(atomicAdd(&cnt[bucket_of(k[j])], 1u), 255u) << (8 * (j & 3));
+        if (e < n) rank8[j >> 2] |= min(atomicAdd(&cnt[bucket_of(k[j])], 1u), 255u) << (8 * (j & 3));
     }
     __syncthreads();
     // exclusive scan of the NB counters (BPT consecutive counters per thread) + largest bucket
@@ -516,13 +515,13 @@ __device__ __forceinline__ void tile_sort_smem(const unsigned long long* g, unsi
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
             const int e = j * NT + tid;
-            if (j < rows && e < n) s[e] = k[j];
+            if (e < n) s[e] = k[j];
         }
         __syncthreads();
-        radix_sort_smem<NT, ITEMS>(s, hist, digit_base, red, n, false);
-        if (red[0] != 0u) {   // long runs of equal depth: sort again on all 64 bits
+        for (bool full64 = false;; full64 = true) {     // one inlined copy; second trip only for long equal-depth runs
+            radix_sort_smem<NT, ITEMS>(s, hist, digit_base, red, n, full64);
+            if (full64 || red[0] == 0u) break;
             __syncthreads();
-            radix_sort_smem<NT, ITEMS>(s, hist, digit_base, red, n, true);
         }
         return;
     }
@@ -536,7 +535,7 @@ __device__ __forceinline__ void tile_sort_smem(const unsigned long long* g, unsi
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         const int e = j * NT + tid;
-        if (j < rows && e < n) s[cnt[bucket_of(k[j])] + ((rank8[j >> 2] >> (8 * (j & 3))) & 0xffu)] = k[j];
+        if (e < n) s[cnt[bucket_of(k[j])] + ((rank8[j >> 2] >> (8 * (j & 3))) & 0xffu)] = k[j];
     }
     __syncthreads();
     // s is now ordered bucket by bucket.  Each thread takes the keys at ITS positions (the registers'
@@ -547,7 +546,7 @@ __device__ __forceinline__ void tile_sort_smem(const unsigned long long* g, unsi
     for (int j = 0; j < ITEMS; ++j) {
         const int e = j * NT + tid;
         uint32_t pos = 0u;
-        if (j < rows && e < n) {
+        if (e < n) {
             const unsigned long long x = s[e];
             k[j] = x;
             const uint32_t b = bucket_of(x);
@@ -568,9 +567,20 @@ __device__ __forceinline__ void tile_sort_smem(const unsigned long long* g, unsi
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         const int e = j * NT + tid;
-        if (j < rows && e < n) s[(pos2[j >> 1] >> (16 * (j & 1))) & 0xffffu] = k[j];
+        if (e < n) s[(pos2[j >> 1] >> (16 * (j & 1))) & 0xffffu] = k[j];
     }
     __syncthreads();
+}
+
+// n <= NT * 16 keys; the per-thread item count is a compile-time constant of each instantiation, so
+// short lists do not walk (predicated-off) rows they do not have.  The branch is CTA-uniform.
+template <int NT, int NB>
+__device__ __forceinline__ void tile_sort_smem(const unsigned long long* g, unsigned long long* s, uint32_t* hist,
+                                               uint32_t* digit_base, uint32_t* red, int n) {
+    if (n <= NT * 4) tile_sort_items<NT, 4, NB>(g, s, hist, digit_base, red, n);
+    else if (n <= NT * 8) tile_sort_items<NT, 8, NB>(g, s, hist, digit_base, red, n);
+    else if (n <= NT * 12) tile_sort_items<NT, 12, NB>(g, s, hist, digit_base, red, n);
+    else tile_sort_items<NT, 16, NB>(g, s, hist, digit_base, red, n);
 }
 
 __device__ __forceinline__ int next_pow2(int n) {
@@ -591,7 +601,7 @@ struct SortSmemBig {
 };
 
 // small tiles: n <= 4096, 256 threads x 16 items
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 sort_small_kernel(const uint32_t* __restrict__ header, const uint32_t* __restrict__ work_order,
                   const uint32_t* __restrict__ tile_start, unsigned long long* __restrict__ keys) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -605,7 +615,7 @@ sort_small_kernel(const uint32_t* __restrict__ header, const uint32_t* __restric
         if (end > max_pairs) end = max_pairs;                  // overflow: stay in bounds
         if (beg >= end) continue;
         const int n = (int)(end - beg);
-        tile_sort_smem<256, 16, 2048>(keys + beg, sm.keys, sm.hist, sm.digit_base, sm.red, n);
+        tile_sort_smem<256, 2048>(keys + beg, sm.keys, sm.hist, sm.digit_base, sm.red, n);
         for (int i = threadIdx.x; i < n; i += 256) keys[beg + i] = sm.keys[i];
         __syncthreads();
     }
@@ -631,7 +641,7 @@ sort_big_kernel(const uint32_t* __restrict__ header, const uint32_t* __restrict_
         const int n = (int)(end - beg);
         unsigned long long* gk = keys + beg;
         if (n <= CH) {
-            tile_sort_smem<1024, 16, 8192>(gk, sb, sm.hist, sm.digit_base, sm.red, n);
+            tile_sort_smem<1024, 8192>(gk, sb, sm.hist, sm.digit_base, sm.red, n);
             for (int i = threadIdx.x; i < n; i += 1024) gk[i] = sb[i];
             __syncthreads();
             continue;
@@ -640,7 +650,7 @@ sort_big_kernel(const uint32_t* __restrict__ header, const uint32_t* __restrict_
         const int N = next_pow2(n);
         for (int c0 = 0; c0 < n; c0 += CH) {
             const int m = min(CH, n - c0);
-            tile_sort_smem<1024, 16, 8192>(gk + c0, sb, sm.hist, sm.digit_base, sm.red, m);
+            tile_sort_items<1024, 16, 8192>(gk + c0, sb, sm.hist, sm.digit_base, sm.red, m);
             for (int i = threadIdx.x; i < m; i += 1024) __stcg(gk + c0 + i, sb[i]);
             __syncthreads();
         }
