@@ -349,13 +349,20 @@ def main():
 
     # pair-evaluation counts for the secondary roofline: ONE extra, untimed step with the
     # instrumented kernel instantiations
-    counters = torch.zeros(16, dtype=torch.int64, device=dev)
+    counters = torch.zeros(_lib.STAT_WORDS, dtype=torch.int64, device=dev)
     _lib.debug_counters(counters.data_ptr())
     step(prm)
     torch.cuda.synchronize(dev)
     _lib.debug_counters(None)
-    evals = dict(zip(_lib.STAT_NAMES, [int(x) for x in counters.tolist()]))
-    evals.pop("_9", None)
+    evals = {k: int(x) for k, x in zip(_lib.STAT_NAMES, counters.tolist()) if not k.startswith("_")}
+    balance = {}
+    for side in ("fwd", "bwd"):      # load balance of the persistent kernels (instrumented instantiation, untimed)
+        span = evals.pop(f"{side}_end_ns") - ~evals.pop(f"{side}_not_begin_ns")   # the word holds ~begin (atomicMax = min)
+        busy, workers = evals.pop(f"{side}_busy_ns"), evals.pop(f"{side}_workers")
+        balance[side] = {"workers": workers, "span_us": span / 1e3,
+                         "mean_busy_frac": busy / max(1, workers * span),
+                         "longest_item_us": evals.pop(f"{side}_max_item_ns") / 1e3}
+    balance["bwd"]["most_evals_in_one_item"] = evals.pop("bwd_max_item_evals")
 
     # ---- timed region 1: device-resident inputs --------------------------------------------
     _lib.profile_enable(args.steps)
@@ -484,7 +491,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": mean_ms[dom],
-                         "secondary": secondary_roofline(evals, mean_ms, clk)},
+                         "secondary": secondary_roofline(evals, mean_ms, clk), "load_balance": balance},
             "step_hbm": {"algorithmic_bytes": step_alg, "achieved_gbs": step_alg / (ms_step * 1e-3) / 1e9,
                          "frac": step_alg / (ms_step * 1e-3) / 1e9 / peak},
             "stages_ms": mean_ms,

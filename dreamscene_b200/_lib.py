@@ -51,7 +51,7 @@ class ViewGrads(C.Structure):       # == b200gsr_view_grads
 
 class SavedLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in ("header", "tile_start", "work_order", "n_contrib",
-                                          "keys", "geom", "dgeom", "total")]
+                                          "keys", "geom", "dgeom", "bwd_items", "total")]
 
 
 class ScratchLayout(C.Structure):
@@ -60,7 +60,7 @@ class ScratchLayout(C.Structure):
 
 
 _lib = None
-ABI_VERSION = 2
+ABI_VERSION = 3
 FWD_NO_BACKWARD = 1
 BWD_COMPOSITE, BWD_PROJECT = 1, 2
 
@@ -194,11 +194,15 @@ def profile_collect() -> dict:
 
 
 STAT_NAMES = ("bwd_pairs_evaluated", "bwd_pairs_contributing", "bwd_lane_contributions", "bwd_k1", "bwd_k2",
-              "bwd_k3_4", "bwd_k5_8", "bwd_k9_16", "bwd_k17_32", "_9", "fwd_pairs_evaluated", "fwd_lane_blends")
+              "bwd_k3_4", "bwd_k5_8", "bwd_k9_16", "bwd_k17_32", "_9", "fwd_pairs_evaluated", "fwd_lane_blends",
+              "_12", "_13", "_14", "_15",
+              "fwd_busy_ns", "fwd_end_ns", "fwd_not_begin_ns", "fwd_workers", "fwd_max_item_ns",
+              "bwd_busy_ns", "bwd_end_ns", "bwd_not_begin_ns", "bwd_workers", "bwd_max_item_evals", "bwd_max_item_ns")
+STAT_WORDS = 32
 
 
 def debug_counters(ptr) -> None:
-    """ptr: device pointer to 16 zeroed uint64 (or None to switch the instrumented kernels off)."""
+    """ptr: device pointer to STAT_WORDS (32) zeroed uint64 (or None to switch the instrumented kernels off)."""
     rc = load().b200gsr_debug_counters(C.c_void_p(ptr) if ptr else None)
     if rc:
         raise RuntimeError(last_error())

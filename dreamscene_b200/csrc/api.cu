@@ -141,6 +141,7 @@ int b200gsr_saved_layout_query(int32_t P, int32_t H, int32_t W, uint64_t max_pai
     out->keys = off;        off = align_up(off + ((size_t)max_pairs + 2) * sizeof(uint64_t));
     out->geom = off;        off = align_up(off + (size_t)P * sizeof(GsrRec));
     out->dgeom = off;       off = align_up(off + (with_backward ? (size_t)P * 12 * sizeof(float) : 0));
+    out->bwd_items = off;   off = align_up(off + (with_backward ? (size_t)GSR_BWD_CLASSES * g.ntiles * 8 * sizeof(uint32_t) : 0));
     out->total = off;
     return B200GSR_OK;
 }

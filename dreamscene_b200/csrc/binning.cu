@@ -103,6 +103,7 @@ scan_order_kernel(int ntiles, int ncopies, uint32_t max_pairs, const uint32_t* _
         header[GSR_H_NUM_BIG] = nbig;   // upper bound: includes n == 4096 exactly (clz 19)
         header[GSR_H_NUM_NONEMPTY] = run - bucket_cnt[32];
         for (int k = 0; k < GSR_NQUEUE; ++k) header[GSR_H_BWD_QUEUE + k] = 0u;
+        for (int k = 0; k < GSR_BWD_CLASSES; ++k) header[GSR_H_BWD_FILL + k] = 0u;
         if (host_notify != nullptr) {   // mapped pinned host memory: tell the host the pair count now
             host_notify[1] = total;
             host_notify[2] = total > max_pairs ? 1u : 0u;
@@ -203,6 +204,8 @@ scan_order_fast_kernel(int ntiles, uint32_t max_pairs, const uint32_t* __restric
             header[GSR_H_NUM_NONEMPTY] = nonempty;
 #pragma unroll
             for (int k = 0; k < GSR_NQUEUE; ++k) header[GSR_H_BWD_QUEUE + k] = 0u;
+#pragma unroll
+            for (int k = 0; k < GSR_BWD_CLASSES; ++k) header[GSR_H_BWD_FILL + k] = 0u;
             if (host_notify != nullptr) {   // mapped pinned host memory: tell the host the pair count now
                 host_notify[1] = total;
                 host_notify[2] = total > max_pairs ? 1u : 0u;

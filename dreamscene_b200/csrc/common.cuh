@@ -52,7 +52,22 @@ enum { GSR_H_NUM_PAIRS = 0, GSR_H_MAX_PAIRS = 1, GSR_H_NUM_TILES = 2, GSR_H_OVER
        GSR_H_BWD_QUEUE = 8,       // [8, 8+GSR_NQUEUE): work-queue counters of composite_bwd; zeroed by the
                                   // forward's scan kernel and restored to zero by project_bwd, so a saved
                                   // buffer can be back-propagated any number of times without a memset
-       GSR_H_WORDS = 32 };
+       GSR_H_BWD_FILL = 32,       // [32, 64): items per size class of the backward's work lists (written by the
+                                  // forward's composite kernel, zeroed by its scan kernel)
+       GSR_H_WORDS = 64 };
+// Backward work items = (tile, 8x4-pixel block) pairs that blended at least one entry, binned by the
+// forward into GSR_BWD_CLASSES size classes of the block's consumed list length (two classes per power
+// of two); the backward pops the longest first.  List of class k: bwd_items[k * num_tiles * 8 ...].
+#define GSR_BWD_CLASSES 32
+__host__ __device__ inline int gsr_bwd_class(uint32_t n) {     // n >= 1
+#ifdef __CUDA_ARCH__
+    const int e = 31 - __clz((int)n);
+#else
+    int e = 0; while ((n >> (e + 1)) != 0u) ++e;
+#endif
+    const int k = 2 * e + (e > 0 ? (int)((n >> (e - 1)) & 1u) : 0);
+    return k < GSR_BWD_CLASSES - 1 ? k : GSR_BWD_CLASSES - 1;
+}
 // counters in scratch
 // The tile work queue is split into GSR_NQUEUE sub-queues (tile w lives in queue w % NQUEUE): one
 // shared counter would serialise every fetch at the ~30 ns same-address L2 atomic rate.

@@ -33,6 +33,9 @@ constexpr int kWarps = 8;      // warps per CTA (in the backward kernel just a c
 #ifndef GSR_BWD_DEFAULT_VARIANT
 #define GSR_BWD_DEFAULT_VARIANT 10    // which backward kernel ships (see gsr_launch_composite_bwd)
 #endif
+#ifndef GSR_FWD_ILP
+#define GSR_FWD_ILP 2                 // list entries in flight per warp in the forward (A/B: B200GSR_FWD_VARIANT=51..54)
+#endif
 #ifndef GSR_BWD_KFAST
 #define GSR_BWD_KFAST 2               // fast-path width of the STATS instantiation
 #endif
@@ -66,6 +69,16 @@ __device__ __forceinline__ uint32_t warp_pop(uint32_t* queue, uint32_t limit, ui
     uint32_t item = 0xffffffffu;
     if (lane == 0) gsr_queue_pop(queue, limit, q, tried, item);
     return __shfl_sync(0xffffffffu, item, 0);
+}
+
+// Forward epilogue: a block that blended at least one entry becomes a work item of the backward, filed under
+// the size class of its consumed list length (see GSR_BWD_CLASSES).  `n` is warp-uniform; call from lane 0.
+__device__ __forceinline__ void bwd_item_append(uint32_t* fill, uint32_t* items, int ntiles, uint32_t tile,
+                                                int blk, uint32_t n) {
+    if (items == nullptr || n == 0u) return;
+    const int k = gsr_bwd_class(n);
+    const uint32_t slot = atomicAdd(fill + k, 1u);
+    items[(size_t)k * ntiles * 8 + slot] = tile * 8u + (uint32_t)blk;
 }
 
 // The blending test, shared verbatim by forward and backward so both take identical decisions.
@@ -105,7 +118,18 @@ __device__ __forceinline__ bool cull_pass(float px, float py, uint32_t ext, floa
 
 // slots of the optional diagnostic counters (b200gsr_debug_counters)
 enum { GSR_STAT_BWD_EVAL = 0, GSR_STAT_BWD_CONTRIB = 1, GSR_STAT_BWD_LANES = 2, GSR_STAT_BWD_HIST = 3,   // 3..8
-       GSR_STAT_FWD_EVAL = 10, GSR_STAT_FWD_LANES = 11, GSR_STAT_WORDS = 16 };
+       GSR_STAT_FWD_EVAL = 10, GSR_STAT_FWD_LANES = 11,
+       // load balance of the persistent kernels (globaltimer ns): sum of worker busy time, last exit,
+       // ~(first entry) [so that atomicMax on a zeroed word yields the minimum], workers, largest item
+       GSR_STAT_FWD_BUSY = 16, GSR_STAT_FWD_END = 17, GSR_STAT_FWD_NBEGIN = 18, GSR_STAT_FWD_WORKERS = 19,
+       GSR_STAT_FWD_MAX_ITEM = 20,
+       GSR_STAT_BWD_BUSY = 21, GSR_STAT_BWD_END = 22, GSR_STAT_BWD_NBEGIN = 23, GSR_STAT_BWD_WORKERS = 24,
+       GSR_STAT_BWD_MAX_ITEM = 25, GSR_STAT_BWD_MAX_ITEM_NS = 26, GSR_STAT_WORDS = 32 };
+__device__ __forceinline__ unsigned long long gsr_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // =============================================================================================
 // Forward
@@ -124,7 +148,7 @@ struct __align__(128) SmemCta {
 
 // PARTS = 1: one CTA of 8 warps per tile.  PARTS = 2 (A/B variant): a tile is rendered by two CTAs of 4 warps,
 // each taking an 16x8 half (both gather the whole list; fewer warps per barrier, twice as many barrier groups).
-template <bool SCORE, int PPL, bool STATS, int PARTS = 1>
+template <bool SCORE, int PPL, bool STATS, int PARTS = 1, int ILP = 1>
 __global__ void __launch_bounds__(256 / PPL / PARTS)
 composite_fwd_kernel(int H, int W, int gx, int gy_view, int Hs, int ntiles, const uint32_t* __restrict__ header,
                      const uint32_t* __restrict__ work_order,
@@ -133,9 +157,11 @@ composite_fwd_kernel(int H, int W, int gx, int gy_view, int Hs, int ntiles, cons
                      const float* __restrict__ bg, uint32_t* __restrict__ queue,
                      float* __restrict__ out_color, float* __restrict__ out_depth_alpha,
                      uint32_t* __restrict__ n_contrib, float* __restrict__ score,
-                     unsigned long long* __restrict__ stats) {
+                     unsigned long long* __restrict__ stats, uint32_t* bwd_fill, uint32_t* bwd_items) {
     constexpr int kThreads = 256 / PPL / PARTS;
     unsigned int st_eval = 0, st_lanes = 0;
+    unsigned long long st_t0 = 0, st_item_t0 = 0, st_max_item_ns = 0;
+    if (STATS) st_t0 = gsr_now_ns();
     constexpr int kPer = kChunk / kThreads;   // list entries gathered per thread per chunk
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SmemCta& sm = *reinterpret_cast<SmemCta*>(smem_raw);
@@ -145,6 +171,11 @@ composite_fwd_kernel(int H, int W, int gx, int gy_view, int Hs, int ntiles, cons
     for (;;) {
         // one shared counter over ALL tiles (empty ones included, they come last): measured faster
         // here than the split queue + static empty tiles (0.141 vs 0.157 ms)
+        if (STATS) {
+            const unsigned long long t = gsr_now_ns();
+            if (st_item_t0 && t - st_item_t0 > st_max_item_ns) st_max_item_ns = t - st_item_t0;
+            st_item_t0 = t;
+        }
         if (tid == 0) sm.work = atomicAdd(queue, 1u);
         __syncthreads();
         const uint32_t w = sm.work;
@@ -221,16 +252,14 @@ composite_fwd_kernel(int H, int W, int gx, int gy_view, int Hs, int ntiles, cons
                 uint32_t mask = __ballot_sync(0xffffffffu, pass);
                 const float4* sp = reinterpret_cast<const float4*>(&st[sub * 32]);
                 const uint32_t pos0 = (uint32_t)(c * kChunk + sub * 32 + 1);
-                while (mask) {
-                    const int b = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const float4* rp = sp + 3 * b;
-                    const float4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
+                // One list entry applied to this lane's pixel(s): the T / colour recurrences are the only
+                // dependences between consecutive entries.
+                auto blend = [&](const float4& q1, const float4& q2, const PairEval (&ev)[PPL], int b) {
                     float wsum = 0.f;
                     if (STATS) ++st_eval;
 #pragma unroll
                     for (int q = 0; q < PPL; ++q) {
-                        const PairEval e = eval_pair(q0.x, q0.y, q0.w, q1.x, q1.y, q1.z, X, Y[q]);
+                        const PairEval& e = ev[q];
                         if (e.valid && !done[q]) {
                             const float Tn = T[q] * (1.0f - e.alpha);
                             if (Tn < GSR_T_STOP) {
@@ -251,6 +280,45 @@ composite_fwd_kernel(int H, int W, int gx, int gy_view, int Hs, int ntiles, cons
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
                         if (lane == 0 && wsum != 0.f) atomicAdd(score + __float_as_uint(q2.w), wsum);
+                    }
+                };
+                while (mask) {
+                    const int b = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const float4* rp = sp + 3 * b;
+                    const float4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
+                    if (ILP >= 2) {
+                        // ILP passing entries per trip: the record loads and exponents of the later ones are
+                        // in flight while the first is evaluated (a warp issues in order, so this divides the
+                        // dependent LDS -> FMA -> EX2 latency paid per entry on the longest tile, which bounds
+                        // the kernel: profiles/r02_balance.md).  Same arithmetic and order per entry.
+                        int bb[ILP];
+                        float4 r0[ILP], r1[ILP], r2[ILP];
+                        bb[0] = b; r0[0] = q0; r1[0] = q1; r2[0] = q2;
+                        int have = 1;                                      // warp-uniform
+#pragma unroll
+                        for (int j = 1; j < ILP; ++j) {
+                            const bool more = mask != 0u;
+                            bb[j] = more ? __ffs(mask) - 1 : b;
+                            mask &= mask - 1;                              // 0 stays 0
+                            have += more ? 1 : 0;
+                            const float4* rj = sp + 3 * bb[j];
+                            r0[j] = rj[0]; r1[j] = rj[1]; r2[j] = rj[2];
+                        }
+                        PairEval ev[ILP][PPL];
+#pragma unroll
+                        for (int j = 0; j < ILP; ++j)
+#pragma unroll
+                            for (int q = 0; q < PPL; ++q)
+                                ev[j][q] = eval_pair(r0[j].x, r0[j].y, r0[j].w, r1[j].x, r1[j].y, r1[j].z, X, Y[q]);
+#pragma unroll
+                        for (int j = 0; j < ILP; ++j)
+                            if (j < have) blend(r1[j], r2[j], ev[j], bb[j]);
+                    } else {
+                        PairEval ea[PPL];
+#pragma unroll
+                        for (int q = 0; q < PPL; ++q) ea[q] = eval_pair(q0.x, q0.y, q0.w, q1.x, q1.y, q1.z, X, Y[q]);
+                        blend(q1, q2, ea, b);
                     }
                 }
                 all_done = true;
@@ -273,6 +341,9 @@ composite_fwd_kernel(int H, int W, int gx, int gy_view, int Hs, int ntiles, cons
                 out_depth_alpha[plane + pix] = T[q];
                 n_contrib[pix] = last[q];
             }
+            // this 8x4 block's entry in the backward's work lists (fwd block blk, pixel row set q)
+            const uint32_t nb = __reduce_max_sync(0xffffffffu, last[q]);
+            if (lane == 0) bwd_item_append(bwd_fill, bwd_items, ntiles, tile, ((blk >> 1) * PPL + q) * 2 + (blk & 1), nb);
         }
     }
     if (STATS && stats != nullptr) {
@@ -280,6 +351,14 @@ composite_fwd_kernel(int H, int W, int gx, int gy_view, int Hs, int ntiles, cons
         if (lane == 0) {
             atomicAdd(stats + GSR_STAT_FWD_EVAL, (unsigned long long)st_eval);
             atomicAdd(stats + GSR_STAT_FWD_LANES, (unsigned long long)tl);
+        }
+        if (threadIdx.x == 0) {
+            const unsigned long long t1 = gsr_now_ns();
+            atomicAdd(stats + GSR_STAT_FWD_BUSY, t1 - st_t0);
+            atomicMax(stats + GSR_STAT_FWD_END, t1);
+            atomicMax(stats + GSR_STAT_FWD_NBEGIN, ~st_t0);
+            atomicAdd(stats + GSR_STAT_FWD_WORKERS, 1ull);
+            atomicMax(stats + GSR_STAT_FWD_MAX_ITEM, st_max_item_ns);
         }
     }
 }
@@ -343,7 +422,7 @@ composite_fwd_tma_kernel(int H, int W, int gx, int ntiles, const uint32_t* __res
                          const __grid_constant__ TmaMap tmap,
                          const float* __restrict__ bg, uint32_t* __restrict__ queue,
                          float* __restrict__ out_color, float* __restrict__ out_depth_alpha,
-                         uint32_t* __restrict__ n_contrib) {
+                         uint32_t* __restrict__ n_contrib, uint32_t* bwd_fill, uint32_t* bwd_items) {
     constexpr int kThreads = 256;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SmemFwdTma& sm = *reinterpret_cast<SmemFwdTma*>(smem_raw);
@@ -487,6 +566,8 @@ composite_fwd_tma_kernel(int H, int W, int gx, int ntiles, const uint32_t* __res
             out_depth_alpha[plane + pix] = T;
             n_contrib[pix] = last;
         }
+        const uint32_t nb = __reduce_max_sync(0xffffffffu, last);
+        if ((tid & 31) == 0) bwd_item_append(bwd_fill, bwd_items, ntiles, tile, tid >> 5, nb);
     }
 }
 
@@ -704,7 +785,7 @@ __device__ __forceinline__ void halve2(float (&v)[10], bool hi) {
 }
 
 
-template <int kSlots, int kMinCtas, int KFAST, bool STATS, bool PIPE = false>
+template <int kSlots, int kMinCtas, int KFAST, bool STATS, bool DUAL = false>
 __global__ void __launch_bounds__(kWarps * 32, kMinCtas)
 composite_bwd2_kernel(int H, int W, int gx, int gy_view, int Hs, int ntiles, const uint32_t* __restrict__ header,
                       const uint32_t* __restrict__ work_order,
@@ -714,24 +795,65 @@ composite_bwd2_kernel(int H, int W, int gx, int gy_view, int Hs, int ntiles, con
                       const float* __restrict__ out_depth_alpha,
                       const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dcolor,
                       const float* __restrict__ dL_ddepth_alpha, float* __restrict__ dgeom,
-                      unsigned long long* __restrict__ stats) {
+                      unsigned long long* __restrict__ stats, const uint32_t* __restrict__ bwd_items) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SmemRing<kSlots>& sm = *reinterpret_cast<SmemRing<kSlots>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     GsrRec (*ring)[32] = sm.rec[wid];
     const uint32_t max_pairs = header[GSR_H_MAX_PAIRS];
-    const uint32_t nonempty = header[GSR_H_NUM_NONEMPTY];
+    // Work lists written by the forward: (tile, block) items by size class of the consumed list length.
+    // Lane l holds the END of class (31 - l) in the concatenated longest-first order.
+    uint32_t cls_end = header[GSR_H_BWD_FILL + (GSR_BWD_CLASSES - 1 - lane)];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, cls_end, o);
+        if (lane >= o) cls_end += t;
+    }
+    const uint32_t num_items = __shfl_sync(0xffffffffu, cls_end, 31);
+    const size_t cls_cap = (size_t)ntiles * 8;
+    static_assert(kWarps % GSR_NQUEUE == 0, "static first items must end on a sub-queue boundary");
+    const uint32_t nworkers = gridDim.x * kWarps;            // the first item of every warp is static: no atomic
+    const uint32_t i_first = (nworkers + GSR_NQUEUE - 1) / GSR_NQUEUE;
+    bool first_item = true;
     const int vidx = bwd_value_index(lane);
     const bool commit_lane = (vidx >= 0) && !(lane & 1);
     const size_t plane = (size_t)Hs * W;
     unsigned long long st_eval = 0, st_contrib = 0, st_lanes = 0;
     unsigned long long st_hist[6] = {0, 0, 0, 0, 0, 0};
+    unsigned long long st_t0 = 0, st_item_eval0 = 0, st_item_t0 = 0, st_max_item = 0, st_max_item_ns = 0;
+    if (STATS) st_t0 = gsr_now_ns();
 
     uint32_t qsel = (blockIdx.x * kWarps + wid) % GSR_NQUEUE, qtried = 0;
     for (;;) {
-        const uint32_t item = warp_pop(queue, nonempty * 8u, qsel, qtried, lane);   // empty tiles: no gradient
-        if (item == 0xffffffffu) break;
-        const uint32_t tile = work_order[item >> 3];
+        if (STATS) {
+            if (st_eval - st_item_eval0 > st_max_item) st_max_item = st_eval - st_item_eval0;
+            const unsigned long long t = gsr_now_ns();
+            if (st_item_t0 && t - st_item_t0 > st_max_item_ns) st_max_item_ns = t - st_item_t0;
+            st_item_eval0 = st_eval; st_item_t0 = t;
+        }
+        // position w in the longest-first order: warp g starts with w = g, later ones come from the split queue
+        uint32_t w;
+        if (first_item) {
+            first_item = false;
+            w = blockIdx.x * kWarps + wid;
+            if (w >= num_items) break;
+        } else {
+            uint32_t i = 0xffffffffu;
+            if (lane == 0) {
+                while (qtried < GSR_NQUEUE) {
+                    const uint32_t cand = (atomicAdd(queue + qsel, 1u) + i_first) * GSR_NQUEUE + qsel;
+                    if (cand < num_items) { i = cand; break; }
+                    qsel = (qsel + 1) % GSR_NQUEUE;
+                    ++qtried;
+                }
+            }
+            w = __shfl_sync(0xffffffffu, i, 0);
+            if (w == 0xffffffffu) break;
+        }
+        const int cdone = __popc(__ballot_sync(0xffffffffu, cls_end <= w));          // classes entirely before w
+        const uint32_t cstart = __shfl_sync(0xffffffffu, cls_end, (cdone + 31) & 31);
+        const uint32_t item = __ldg(bwd_items + (size_t)(GSR_BWD_CLASSES - 1 - cdone) * cls_cap + (w - (cdone ? cstart : 0u)));
+        const uint32_t tile = item >> 3;
         const int blk = (int)(item & 7u);
         uint32_t beg = tile_start[tile], end = tile_start[tile + 1];
         if (end > max_pairs) end = max_pairs;
@@ -803,71 +925,97 @@ composite_bwd2_kernel(int H, int W, int gx, int gy_view, int Hs, int ntiles, con
             const float4* sp = reinterpret_cast<const float4*>(st);
             const uint32_t pos0 = (uint32_t)(sidx * 32 + 1);
 #ifndef GSR_EXACT_EXP
-            if (PIPE) {
-                // Software-pipelined form of the loop below: the record loads and the exponent of the NEXT
-                // passing entry are issued before the current entry's body + butterfly run, so their LDS /
-                // MUFU latency hides behind ~100 independent instructions.  Decisions are unchanged.
-                struct Ev { float2 d; float A, Bq, Cq, op, depth, G, p2; const float4* rp; uint32_t pos; };
-                auto issue = [&](Ev& e) {
-                    const int b = 31 - __clz(mask);
-                    mask &= ~(1u << b);
-                    e.rp = sp + 3 * b;
-                    const float4 q0 = e.rp[0], q1 = e.rp[1];
-                    e.pos = pos0 + (uint32_t)b;
-                    e.d = __fadd2_rn(make_float2(q0.x, q0.y), XY);
-                    e.A = q0.w; e.Bq = q1.x; e.Cq = q1.y; e.op = q1.z; e.depth = q1.w;
-                    const float u = __fmaf_rn(e.A, e.d.x, __fmul_rn(e.Bq, e.d.y));
-                    e.p2 = __fmaf_rn(__fmul_rn(e.Cq, e.d.y), e.d.y, __fmul_rn(u, e.d.x));
-                    e.G = ex2_approx(e.p2);
+            if (DUAL) {
+                // Two passing entries per trip.  A warp issues in order, so with one entry per trip every
+                // dependent step (LDS -> FMA -> EX2 -> ballot -> body -> 5 shuffle levels) is paid in full per
+                // entry; the longest (tile, block) item - a serial chain of several hundred entries - bounds the
+                // kernel (profiles/r02_balance.md).  Here both entries' loads, exponents and butterflies are
+                // independent instruction streams the scheduler interleaves; only the T / accumulated-colour
+                // recurrences stay serial.  Per-entry arithmetic and decisions are unchanged.
+                auto alpha_of = [&](const float4& q0, const float4& q1, float2& d, float& G, float& alpha) {
+                    d = __fadd2_rn(make_float2(q0.x, q0.y), XY);
+                    const float u = __fmaf_rn(q0.w, d.x, __fmul_rn(q1.x, d.y));
+                    const float p2 = __fmaf_rn(__fmul_rn(q1.y, d.y), d.y, __fmul_rn(u, d.x));
+                    G = ex2_approx(p2);
+                    alpha = fminf(GSR_ALPHA_MAX, __fmul_rn(q1.z, G));
+                    return (p2 <= 0.0f) && (alpha >= GSR_ALPHA_MIN);
                 };
-                Ev cur, nxt;
-                bool have = mask != 0u;
-                if (have) issue(cur);
-                while (have) {
-                    const bool have_next = mask != 0u;
-                    if (have_next) issue(nxt);
-                    const float alpha = fminf(GSR_ALPHA_MAX, __fmul_rn(cur.op, cur.G));
-                    const bool contrib = (cur.p2 <= 0.0f) && (alpha >= GSR_ALPHA_MIN) && cur.pos <= last;
-                    const uint32_t cm = __ballot_sync(0xffffffffu, contrib);
-                    if (cm != 0u) {
-                        const float4 q2 = cur.rp[2];
-                        const float2 d = cur.d;
-                        const float am = contrib ? alpha : 0.0f;
-                        const float Gm = contrib ? cur.G : 0.0f;
-                        const float rom = rcp_approx(1.0f - am);
-                        T = contrib ? T * rom : T;
-                        const float wgt = am * T;
-                        const float2 c01 = make_float2(q2.x, q2.y), c2D = make_float2(q2.z, cur.depth);
-                        const float2 d01 = __fadd2_rn(c01, make_float2(-acc01.x, -acc01.y));
-                        const float2 d2D = __fadd2_rn(c2D, make_float2(-acc2D.x, -acc2D.y));
-                        const float2 dot2 = __ffma2_rn(d2D, dC2D, __fmul2_rn(d01, dC01));
-                        const float dLda = (dot2.x + dot2.y) * T - bgT * rom;
-                        const float2 am2 = make_float2(am, am);
-                        acc01 = __ffma2_rn(am2, d01, acc01);
-                        acc2D = __ffma2_rn(am2, d2D, acc2D);
-                        float vv[10];
-                        vv[5] = Gm * dLda;
-                        const float gG = cur.op * vv[5];
-                        const float2 gs = __ffma2_rn(make_float2(cur.A + cur.A, cur.Cq + cur.Cq), d,
-                                                     __fmul2_rn(make_float2(cur.Bq, cur.Bq), make_float2(d.y, d.x)));
-                        const float2 gG2 = make_float2(gG, gG);
-                        const float2 v01 = __fmul2_rn(gG2, gs);
-                        const float2 tu = __fmul2_rn(gG2, d);
-                        const float2 v24 = __fmul2_rn(tu, d);
-                        vv[0] = v01.x; vv[1] = v01.y; vv[2] = v24.x; vv[3] = tu.x * d.y; vv[4] = v24.y;
-                        const float2 w2 = make_float2(wgt, wgt);
-                        const float2 v67 = __fmul2_rn(w2, dC01), v89 = __fmul2_rn(w2, dC2D);
-                        vv[6] = v67.x; vv[7] = v67.y; vv[8] = v89.x; vv[9] = v89.y;
-                        float* row = dgeom + 12 * (size_t)__float_as_uint(q2.w);
-                        halve2<10, 16>(vv, lane & 16);
-                        halve2<5, 8>(vv, lane & 8);
-                        halve2<3, 4>(vv, lane & 4);
-                        halve2<2, 2>(vv, lane & 2);
-                        const float tot = vv[0] + __shfl_xor_sync(0xffffffffu, vv[0], 1);
-                        if (commit_lane) atomicAdd(row + vidx, tot);
+                auto body = [&](const float4& q0, const float4& q1, const float4& q2, const float2& d, float G,
+                                float alpha, bool contrib, float (&vv)[10]) {
+                    const float am = contrib ? alpha : 0.0f;
+                    const float Gm = contrib ? G : 0.0f;
+                    const float rom = rcp_approx(1.0f - am);
+                    T = contrib ? T * rom : T;
+                    const float wgt = am * T;
+                    const float2 c01 = make_float2(q2.x, q2.y), c2D = make_float2(q2.z, q1.w);
+                    const float2 d01 = __fadd2_rn(c01, make_float2(-acc01.x, -acc01.y));
+                    const float2 d2D = __fadd2_rn(c2D, make_float2(-acc2D.x, -acc2D.y));
+                    const float2 dot2 = __ffma2_rn(d2D, dC2D, __fmul2_rn(d01, dC01));
+                    const float dLda = (dot2.x + dot2.y) * T - bgT * rom;
+                    const float2 am2 = make_float2(am, am);
+                    acc01 = __ffma2_rn(am2, d01, acc01);
+                    acc2D = __ffma2_rn(am2, d2D, acc2D);
+                    vv[5] = Gm * dLda;
+                    const float gG = q1.z * vv[5];
+                    const float2 gs = __ffma2_rn(make_float2(q0.w + q0.w, q1.y + q1.y), d,
+                                                 __fmul2_rn(make_float2(q1.x, q1.x), make_float2(d.y, d.x)));
+                    const float2 gG2 = make_float2(gG, gG);
+                    const float2 v01 = __fmul2_rn(gG2, gs);
+                    const float2 tu = __fmul2_rn(gG2, d);
+                    const float2 v24 = __fmul2_rn(tu, d);
+                    vv[0] = v01.x; vv[1] = v01.y; vv[2] = v24.x; vv[3] = tu.x * d.y; vv[4] = v24.y;
+                    const float2 w2 = make_float2(wgt, wgt);
+                    const float2 v67 = __fmul2_rn(w2, dC01), v89 = __fmul2_rn(w2, dC2D);
+                    vv[6] = v67.x; vv[7] = v67.y; vv[8] = v89.x; vv[9] = v89.y;
+                };
+                while (mask) {
+                    const int b0 = 31 - __clz(mask);
+                    mask &= ~(1u << b0);
+                    const bool two = mask != 0u;                          // warp-uniform
+                    const int b1 = two ? 31 - __clz(mask) : b0;
+                    mask &= ~(1u << b1);
+                    const float4* rpa = sp + 3 * b0;
+                    const float4* rpb = sp + 3 * b1;
+                    const float4 a0 = rpa[0], a1 = rpa[1], c0 = rpb[0], c1 = rpb[1];
+                    float2 da, db;
+                    float Ga, Gb, alpa, alpb;
+                    const bool va = alpha_of(a0, a1, da, Ga, alpa);
+                    const bool vb = alpha_of(c0, c1, db, Gb, alpb);
+                    const bool ca = va && (pos0 + (uint32_t)b0) <= last;
+                    const bool cb = two && vb && (pos0 + (uint32_t)b1) <= last;
+                    const uint32_t cma = __ballot_sync(0xffffffffu, ca);
+                    const uint32_t cmb = __ballot_sync(0xffffffffu, cb);
+                    if ((cma | cmb) == 0u) continue;
+                    float wa[10], wb[10];
+                    float *rowa = dgeom, *rowb = dgeom;
+                    if (cma != 0u) {
+                        const float4 a2 = rpa[2];
+                        body(a0, a1, a2, da, Ga, alpa, ca, wa);
+                        rowa = dgeom + 12 * (size_t)__float_as_uint(a2.w);
                     }
-                    cur = nxt;
-                    have = have_next;
+                    if (cmb != 0u) {
+                        const float4 c2 = rpb[2];
+                        body(c0, c1, c2, db, Gb, alpb, cb, wb);
+                        rowb = dgeom + 12 * (size_t)__float_as_uint(c2.w);
+                    }
+                    if (cma != 0u && cmb != 0u) {
+                        halve2<10, 16>(wa, lane & 16); halve2<10, 16>(wb, lane & 16);
+                        halve2<5, 8>(wa, lane & 8);    halve2<5, 8>(wb, lane & 8);
+                        halve2<3, 4>(wa, lane & 4);    halve2<3, 4>(wb, lane & 4);
+                        halve2<2, 2>(wa, lane & 2);    halve2<2, 2>(wb, lane & 2);
+                        const float ta = wa[0] + __shfl_xor_sync(0xffffffffu, wa[0], 1);
+                        const float tb = wb[0] + __shfl_xor_sync(0xffffffffu, wb[0], 1);
+                        if (commit_lane) { atomicAdd(rowa + vidx, ta); atomicAdd(rowb + vidx, tb); }
+                    } else {
+                        float (&w1)[10] = cma != 0u ? wa : wb;
+                        float* row1 = cma != 0u ? rowa : rowb;
+                        halve2<10, 16>(w1, lane & 16);
+                        halve2<5, 8>(w1, lane & 8);
+                        halve2<3, 4>(w1, lane & 4);
+                        halve2<2, 2>(w1, lane & 2);
+                        const float t1 = w1[0] + __shfl_xor_sync(0xffffffffu, w1[0], 1);
+                        if (commit_lane) atomicAdd(row1 + vidx, t1);
+                    }
                 }
             } else
 #endif
@@ -957,6 +1105,13 @@ composite_bwd2_kernel(int H, int W, int gx, int gy_view, int Hs, int ntiles, con
         atomicAdd(stats + GSR_STAT_BWD_LANES, st_lanes);
 #pragma unroll
         for (int j = 0; j < 6; ++j) atomicAdd(stats + GSR_STAT_BWD_HIST + j, st_hist[j]);
+        const unsigned long long t1 = gsr_now_ns();
+        atomicAdd(stats + GSR_STAT_BWD_BUSY, t1 - st_t0);
+        atomicMax(stats + GSR_STAT_BWD_END, t1);
+        atomicMax(stats + GSR_STAT_BWD_NBEGIN, ~st_t0);
+        atomicAdd(stats + GSR_STAT_BWD_WORKERS, 1ull);
+        atomicMax(stats + GSR_STAT_BWD_MAX_ITEM, st_max_item);
+        atomicMax(stats + GSR_STAT_BWD_MAX_ITEM_NS, st_max_item_ns);
     }
 }
 
@@ -969,6 +1124,7 @@ struct CompPtrs {
     const unsigned long long* keys;
     const GsrRec* geom;
     uint32_t* n_contrib;
+    uint32_t *bwd_fill, *bwd_items;   // backward work lists (items == nullptr: the forward was issued without backward)
 };
 static CompPtrs comp_ptrs(const uint8_t* saved, const b200gsr_saved_layout& vl, int H, int W, int num_views, int gy_view) {
     CompPtrs c;
@@ -984,18 +1140,20 @@ static CompPtrs comp_ptrs(const uint8_t* saved, const b200gsr_saved_layout& vl, 
     c.keys = reinterpret_cast<const unsigned long long*>(saved + vl.keys);
     c.geom = reinterpret_cast<const GsrRec*>(saved + vl.geom);
     c.n_contrib = reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(saved) + vl.n_contrib);
+    c.bwd_fill = reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(saved) + vl.header) + GSR_H_BWD_FILL;
+    c.bwd_items = vl.bwd_items < vl.total ? reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(saved) + vl.bwd_items) : nullptr;
     return c;
 }
 
-template <bool SCORE, bool STATS>
+template <bool SCORE, bool STATS, int ILP = 1>
 static cudaError_t launch_fwd(const GsrFwdArgs& a, int nblocks, const CompPtrs& c, uint32_t* queue) {
     const int smem = (int)sizeof(SmemCta);
     static std::atomic<unsigned long long> attr_done{0};
-    cudaError_t e = gsr_smem_once(composite_fwd_kernel<SCORE, 1, STATS>, smem, attr_done);
+    cudaError_t e = gsr_smem_once(composite_fwd_kernel<SCORE, 1, STATS, 1, ILP>, smem, attr_done);
     if (e != cudaSuccess) return e;
-    composite_fwd_kernel<SCORE, 1, STATS><<<nblocks, 256, smem, a.stream>>>(
+    composite_fwd_kernel<SCORE, 1, STATS, 1, ILP><<<nblocks, 256, smem, a.stream>>>(
         a.prm.image_height, a.prm.image_width, c.grid.gx, a.gy_view, c.H, c.grid.ntiles, c.header, c.work_order, c.tile_start,
-        c.keys, c.geom, a.prm.bg, queue, a.out_color, a.out_depth_alpha, c.n_contrib, a.score, a.stats);
+        c.keys, c.geom, a.prm.bg, queue, a.out_color, a.out_depth_alpha, c.n_contrib, a.score, a.stats, c.bwd_fill, c.bwd_items);
     return cudaGetLastError();
 }
 
@@ -1034,7 +1192,7 @@ static cudaError_t launch_fwd_tma(const GsrFwdArgs& a, int nblocks, const CompPt
     if (VARIANT == 2 && (e = make_geom_tensor_map(c.geom, a.prm.P, &tmap)) != cudaSuccess) return e;
     composite_fwd_tma_kernel<VARIANT><<<nblocks, 256, smem, a.stream>>>(
         a.prm.image_height, a.prm.image_width, c.grid.gx, c.grid.ntiles, c.header, c.work_order, c.tile_start,
-        c.keys, c.geom, tmap, a.prm.bg, queue, a.out_color, a.out_depth_alpha, c.n_contrib);
+        c.keys, c.geom, tmap, a.prm.bg, queue, a.out_color, a.out_depth_alpha, c.n_contrib, c.bwd_fill, c.bwd_items);
     return cudaGetLastError();
 }
 
@@ -1045,6 +1203,12 @@ cudaError_t gsr_launch_composite_fwd(const GsrFwdArgs& a) {
     const int nblocks = min(c.grid.ntiles, a.num_sms * 6);
     // B200GSR_FWD_VARIANT = 1 | 2: bulk-copy / TMA staging experiments (profiles/r02_tma_ab.md)
     static const int fwd_variant = [] { const char* e = getenv("B200GSR_FWD_VARIANT"); return e ? atoi(e) : 0; }();
+    if (fwd_variant >= 51 && fwd_variant <= 54 && !a.prm.score_flag && a.stats == nullptr) {   // 1/2/3/4 list entries in flight
+        return fwd_variant == 51 ? launch_fwd<false, false, 1>(a, nblocks, c, queue)
+             : fwd_variant == 52 ? launch_fwd<false, false, 2>(a, nblocks, c, queue)
+             : fwd_variant == 53 ? launch_fwd<false, false, 3>(a, nblocks, c, queue)
+                                 : launch_fwd<false, false, 4>(a, nblocks, c, queue);
+    }
     if (fwd_variant == 4 && !a.prm.score_flag && a.stats == nullptr) {     // two 4-warp CTAs per tile
         const int smem = (int)sizeof(SmemCta);
         static std::atomic<unsigned long long> attr_done4{0};
@@ -1053,7 +1217,7 @@ cudaError_t gsr_launch_composite_fwd(const GsrFwdArgs& a) {
         const int nb4 = min(2 * c.grid.ntiles, a.num_sms * 8);
         composite_fwd_kernel<false, 1, false, 2><<<nb4, 128, smem, a.stream>>>(
             a.prm.image_height, a.prm.image_width, c.grid.gx, a.gy_view, c.H, c.grid.ntiles, c.header, c.work_order, c.tile_start,
-            c.keys, c.geom, a.prm.bg, queue, a.out_color, a.out_depth_alpha, c.n_contrib, a.score, a.stats);
+            c.keys, c.geom, a.prm.bg, queue, a.out_color, a.out_depth_alpha, c.n_contrib, a.score, a.stats, c.bwd_fill, c.bwd_items);
         return cudaGetLastError();
     }
     if (fwd_variant != 0 && !a.prm.score_flag && a.stats == nullptr && a.num_views == 1) {
@@ -1061,8 +1225,10 @@ cudaError_t gsr_launch_composite_fwd(const GsrFwdArgs& a) {
         return fwd_variant == 2 ? launch_fwd_tma<2>(a, nb, c, queue) : launch_fwd_tma<1>(a, nb, c, queue);
     }
     if (a.stats != nullptr)
-        return a.prm.score_flag ? launch_fwd<true, true>(a, nblocks, c, queue) : launch_fwd<false, true>(a, nblocks, c, queue);
-    return a.prm.score_flag ? launch_fwd<true, false>(a, nblocks, c, queue) : launch_fwd<false, false>(a, nblocks, c, queue);
+        return a.prm.score_flag ? launch_fwd<true, true, GSR_FWD_ILP>(a, nblocks, c, queue)
+                                : launch_fwd<false, true, GSR_FWD_ILP>(a, nblocks, c, queue);
+    return a.prm.score_flag ? launch_fwd<true, false, GSR_FWD_ILP>(a, nblocks, c, queue)
+                            : launch_fwd<false, false, GSR_FWD_ILP>(a, nblocks, c, queue);
 }
 
 template <int kSlots, int kMinCtas>
@@ -1078,17 +1244,17 @@ static cudaError_t launch_bwd(const GsrBwdArgs& a, const CompPtrs& c, uint32_t* 
     return cudaGetLastError();
 }
 
-template <int kSlots, int kMinCtas, int KFAST, bool STATS, bool PIPE = false>
+template <int kSlots, int kMinCtas, int KFAST, bool STATS, bool DUAL = false>
 static cudaError_t launch_bwd2(const GsrBwdArgs& a, const CompPtrs& c, uint32_t* queue, float* dgeom) {
     const int smem = (int)sizeof(SmemRing<kSlots>);
     const int nblocks = min(c.grid.ntiles, a.num_sms * kMinCtas);
     static std::atomic<unsigned long long> attr_done{0};
-    cudaError_t e = gsr_smem_once(composite_bwd2_kernel<kSlots, kMinCtas, KFAST, STATS, PIPE>, smem, attr_done);
+    cudaError_t e = gsr_smem_once(composite_bwd2_kernel<kSlots, kMinCtas, KFAST, STATS, DUAL>, smem, attr_done);
     if (e != cudaSuccess) return e;
-    composite_bwd2_kernel<kSlots, kMinCtas, KFAST, STATS, PIPE><<<nblocks, kWarps * 32, smem, a.stream>>>(
+    composite_bwd2_kernel<kSlots, kMinCtas, KFAST, STATS, DUAL><<<nblocks, kWarps * 32, smem, a.stream>>>(
         a.prm.image_height, a.prm.image_width, c.grid.gx, a.gy_view, c.H, c.grid.ntiles, c.header, c.work_order, c.tile_start,
         c.keys, c.geom, a.prm.bg, queue, a.out_depth_alpha, c.n_contrib, a.dL_dcolor, a.dL_ddepth_alpha, dgeom,
-        a.stats);
+        a.stats, c.bwd_items);
     return cudaGetLastError();
 }
 
@@ -1108,8 +1274,9 @@ cudaError_t gsr_launch_composite_bwd(const GsrBwdArgs& a) {
         case 12: return launch_bwd2<3, 4, 2, false>(a, c, queue, dgeom);
         case 14: return launch_bwd2<3, 4, 4, false>(a, c, queue, dgeom);
         case 125: return launch_bwd2<3, 5, 2, false>(a, c, queue, dgeom);
-        case 20: return launch_bwd2<3, 4, 0, false, true>(a, c, queue, dgeom);     // software-pipelined body
-        case 23: return launch_bwd2<3, 3, 0, false, true>(a, c, queue, dgeom);     // ... with 85 registers, 3 CTAs/SM
+        case 30: return launch_bwd2<3, 4, 0, false, true>(a, c, queue, dgeom);     // two entries in flight per warp, 64 registers
+        case 33: return launch_bwd2<3, 3, 0, false, true>(a, c, queue, dgeom);     // ... 3 CTAs/SM (85 registers)
+        case 32: return launch_bwd2<3, 2, 0, false, true>(a, c, queue, dgeom);     // ... 2 CTAs/SM (128 registers)
         default: break;
     }
     static const int slots = [] { const char* e = getenv("B200GSR_BWD_SLOTS"); return e ? atoi(e) : 3; }();

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define B200GSR_VERSION 2
+#define B200GSR_VERSION 3
 
 /* error codes */
 #define B200GSR_OK 0
@@ -70,9 +70,10 @@ typedef struct b200gsr_params {
 
 /* Byte offsets of the arrays inside the `saved` buffer (for tests / debugging / backward). */
 typedef struct b200gsr_saved_layout {
-    size_t header;        /* uint32[32]: [0]=num_pairs (true D, may exceed max_pairs) [1]=max_pairs
+    size_t header;        /* uint32[64]: [0]=num_pairs (true D, may exceed max_pairs) [1]=max_pairs
                              [2]=num_tiles [3]=overflow flag [4]=num_big_tiles [5]=non-empty tiles
-                             [8..15]=backward work-queue counters (zero between calls) rest reserved */
+                             [8..15]=backward work-queue counters (zero between calls)
+                             [32..63]=items per size class of bwd_items; rest reserved */
     size_t tile_start;    /* uint32[num_tiles+1] exclusive prefix of per-tile pair counts */
     size_t work_order;    /* uint32[num_tiles] tile ids, longest list first */
     size_t n_contrib;     /* uint32[H*W] index(1-based) of the last blended entry per pixel */
@@ -82,6 +83,10 @@ typedef struct b200gsr_saved_layout {
                              Gaussians are zeroed by the forward and restored to zero by the backward
                              (read-and-clear), so no memset is ever needed.  Absent (size 0) when the
                              layout is queried with with_backward = 0 */
+    size_t bwd_items;     /* uint32[32][num_tiles*8] work lists of the backward: (tile*8 + 8x4-pixel block) of
+                             every block that blended an entry, by size class of its consumed list length
+                             (written by the forward; longest class popped first).  Absent with
+                             with_backward = 0 */
     size_t total;
 } b200gsr_saved_layout;
 
@@ -342,6 +347,9 @@ int b200gsr_profile_enable(int32_t max_calls);
  *   [2] contributing (pixel, Gaussian) pairs              [3..8] histogram of contributing lanes per
  *   pair: 1, 2, 3-4, 5-8, 9-16, 17-32                     [10] pairs evaluated by the forward
  *   [11] blended (pixel, Gaussian) pairs in the forward.
+ *   [16..20] forward load balance (globaltimer ns): sum of CTA busy time, last exit, ~(first entry), CTAs,
+ *   longest tile;  [21..26] the same for the backward's warps + most evaluations / longest time of one item.
+ * The buffer holds 32 zeroed uint64.
  * bench.py uses them (outside the timed region) for the pair-evaluation roofline.  NULL switches back.
  */
 int b200gsr_debug_counters(unsigned long long* device_counters);

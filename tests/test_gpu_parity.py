@@ -118,6 +118,44 @@ def test_cfg1_forward_and_indices_10k_256():
     assert U.rel_err(cu["score"], ref["score"]) < 1e-4
 
 
+def test_backward_work_lists_cover_every_blended_block_once():
+    """The forward files every 8x4-pixel block that blended an entry under the size class of its consumed list
+    length (common.cuh::gsr_bwd_class); the backward pops the classes longest first.  Checked against the
+    n_contrib plane of the same forward: exact multiset of (class, tile*8 + block)."""
+    from dreamscene_b200 import rasterizer as R
+    sc, cam, deg = U.make_inputs(20000, 200, 136, seed=5)          # ragged image: partial tiles at both edges
+    H, W = cam.image_height, cam.image_width
+    dev = torch.device("cuda", torch.cuda.current_device())
+    S = U.cuda_settings(cam, deg)
+    t = {k: v.to(dev) for k, v in sc.items()}
+    color, radii, da, _, st = R._forward_impl(S, t["means3D"], t["shs"], None, t["opacities"], t["scales"],
+                                              t["rotations"], None, with_backward=True)
+    torch.cuda.synchronize()
+    dec = U.decode_saved(st.saved, sc["means3D"].shape[0], H, W, st.capacity)
+    gx, gy = (W + 15) // 16, (H + 15) // 16
+    nc = np.zeros((gy * 16, gx * 16), np.int64)
+    nc[:H, :W] = dec["n_contrib"]
+    # block index inside the tile: (blk & 1) -> x half (8 px), (blk >> 1) -> y quarter (4 px)
+    nb = nc.reshape(gy, 4, 4, gx, 2, 8).max(axis=(2, 5))           # [ty, yq, tx, xh]
+    expect = set()
+    for ty in range(gy):
+        for yq in range(4):
+            for tx in range(gx):
+                for xh in range(2):
+                    n = int(nb[ty, yq, tx, xh])
+                    if n > 0:
+                        e = n.bit_length() - 1
+                        k = min(31, 2 * e + (((n >> (e - 1)) & 1) if e > 0 else 0))
+                        expect.add((k, (ty * gx + tx) * 8 + yq * 2 + xh))
+    got = set()
+    for k in range(32):
+        for it in dec["bwd_items"][k, :dec["bwd_fill"][k]]:
+            assert (k, int(it)) not in got
+            got.add((k, int(it)))
+    assert got == expect and len(expect) > 50
+    assert len({k for k, _ in expect}) >= 4                        # several size classes in use
+
+
 def test_backward_matches_fp64_oracle_on_fp32_lists():
     sc, cam, deg = U.make_inputs(3000, 128, 128, seed=3)
     H = W = 128

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert set(_lib.EXPORTS) == set(syms)
     for s in syms:
         assert hasattr(lib, s), s
-    assert lib.b200gsr_version() == 2
+    assert lib.b200gsr_version() == 3
 
 
 def test_layout_queries_are_monotone_and_aligned():

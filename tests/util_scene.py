@@ -49,7 +49,11 @@ def decode_saved(saved: torch.Tensor, P, H, W, cap):
     n = min(D, cap)
     keys = raw[vl.keys:vl.keys + 8 * n].view(np.uint64)
     geom = raw[vl.geom:vl.geom + 48 * P].view(np.uint32).reshape(P, 12)
+    fill = raw[vl.header + 4 * 32:vl.header + 4 * 64].view(np.uint32).astype(np.int64)     # backward work lists
+    items = raw[vl.bwd_items:vl.bwd_items + 4 * 32 * ntiles * 8].view(np.uint32).reshape(32, ntiles * 8) \
+        if vl.bwd_items < vl.total and len(raw) >= vl.total else None
     return dict(num_pairs=D, header=header.copy(), tile_start=ts, work_order=wo, n_contrib=nc,
+                bwd_fill=fill, bwd_items=items,
                 idx=(keys & np.uint64(0xFFFFFFFF)).astype(np.int64),
                 depth_bits=(keys >> np.uint64(32)).astype(np.uint32), geom_f32=geom.view(np.float32))
 
