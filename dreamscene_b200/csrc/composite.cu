@@ -1209,6 +1209,25 @@ cudaError_t gsr_launch_composite_fwd(const GsrFwdArgs& a) {
              : fwd_variant == 53 ? launch_fwd<false, false, 3>(a, nblocks, c, queue)
                                  : launch_fwd<false, false, 4>(a, nblocks, c, queue);
     }
+    if ((fwd_variant == 42 || fwd_variant == 44) && !a.prm.score_flag && a.stats == nullptr) {
+        // a tile rendered by 2 (4) CTAs of 4 (2) warps, two entries in flight: finer work items for the balance
+        const int smem = (int)sizeof(SmemCta);
+        static std::atomic<unsigned long long> attr_done42{0}, attr_done44{0};
+        if (fwd_variant == 42) {
+            cudaError_t e4 = gsr_smem_once(composite_fwd_kernel<false, 1, false, 2, 2>, smem, attr_done42);
+            if (e4 != cudaSuccess) return e4;
+            composite_fwd_kernel<false, 1, false, 2, 2><<<min(2 * c.grid.ntiles, a.num_sms * 8), 128, smem, a.stream>>>(
+                a.prm.image_height, a.prm.image_width, c.grid.gx, a.gy_view, c.H, c.grid.ntiles, c.header, c.work_order, c.tile_start,
+                c.keys, c.geom, a.prm.bg, queue, a.out_color, a.out_depth_alpha, c.n_contrib, a.score, a.stats, c.bwd_fill, c.bwd_items);
+        } else {
+            cudaError_t e4 = gsr_smem_once(composite_fwd_kernel<false, 1, false, 4, 2>, smem, attr_done44);
+            if (e4 != cudaSuccess) return e4;
+            composite_fwd_kernel<false, 1, false, 4, 2><<<min(4 * c.grid.ntiles, a.num_sms * 9), 64, smem, a.stream>>>(
+                a.prm.image_height, a.prm.image_width, c.grid.gx, a.gy_view, c.H, c.grid.ntiles, c.header, c.work_order, c.tile_start,
+                c.keys, c.geom, a.prm.bg, queue, a.out_color, a.out_depth_alpha, c.n_contrib, a.score, a.stats, c.bwd_fill, c.bwd_items);
+        }
+        return cudaGetLastError();
+    }
     if (fwd_variant == 4 && !a.prm.score_flag && a.stats == nullptr) {     // two 4-warp CTAs per tile
         const int smem = (int)sizeof(SmemCta);
         static std::atomic<unsigned long long> attr_done4{0};
