@@ -22,7 +22,7 @@ M = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram rd"), ("
      ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ %"),
      ("launch__registers_per_thread", "regs"), ("smsp__inst_executed.sum", "warp inst"),
      ("lts__t_bytes.sum", "L2 bytes")]
-STAGE = {"project_sh": "project_sh", "scan_order": "scan_order", "scatter": "scatter", "multisplit": "scatter", "sort_big": "tile_sort",
+STAGE = {"project_sh": "project_sh", "multisplit<count>": "project_sh", "scan_order": "scan_order", "scatter": "scatter", "sort_big": "tile_sort",
          "sort_small": "tile_sort", "composite_fwd": "composite_fwd", "composite_bwd": "composite_bwd",
          "project_bwd": "project_bwd"}
 
@@ -53,6 +53,8 @@ seen = set()
 for r in data:
     name = r[col["Kernel Name"]].split("(")[0].split("::")[-1].strip()
     short = name.replace("_kernel", "").replace("void ", "").split("<")[0]
+    if short == "multisplit":       # one template, two kernels: <0> counts tile hits (project stage), <1> scatters the keys
+        short = "multisplit<scatter>" if "<1" in name else "multisplit<count>"
     if short in seen:
         continue
     seen.add(short)
