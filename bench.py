@@ -281,6 +281,9 @@ def main():
     ap.add_argument("--reduce", default="backward", choices=["backward", "deferred"],
                     help="N>1: chunk-overlapped all-reduce inside the rasterizer backward, or DDP-style "
                          "all-reduce of the leaf gradients after it (dreamscene_b200.parallel)")
+    ap.add_argument("--sh-exchange", default="factored", choices=["factored", "dense"],
+                    help="N>1, --reduce backward: SH gradient exchanged as [P,3] colour gradients + camera centre "
+                         "(all-gather, rebuilt locally) or all-reduced as [P,M,3] rows")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -301,7 +304,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        parallel.enable_view_sharding(mode=args.reduce)
+        parallel.enable_view_sharding(mode=args.reduce, sh_exchange=args.sh_exchange)
     _lib.load()
 
     sc, cam, gc_h, gd_h = make_scene(wl, rank)
@@ -407,7 +410,7 @@ def main():
             torch.autograd.backward([c_, a_], [gc_v.to(dev), gd_v.to(dev)])
             total += torch.cat([prm[k].grad.reshape(-1) for k in names])
         args.reduce = reduce_mode
-        parallel.enable_view_sharding(mode=args.reduce)
+        parallel.enable_view_sharding(mode=args.reduce, sh_exchange=args.sh_exchange)
         err = ((reduced - total).double().norm() / total.double().norm().clamp_min(1e-300)).reshape(1)
         dist.all_reduce(err, op=dist.ReduceOp.MAX)
         grad_check = {"rel_err_max_over_ranks": float(err.item()), "views_summed": world,
@@ -504,11 +507,18 @@ def main():
             line["grad_check"] = grad_check
             ncoef = (args.sh_degree + 1) ** 2
             floats = 3 + 1 + 3 * ncoef + 3 + 4
-            line["limiting_collective"] = (
-                f"ncclAllReduce(SUM, fp32) of the parameter gradients: {floats} floats/Gaussian = {floats * 4 * P / 1e6:.0f} MB/step "
-                + ("one call on the rasterizer's flat gradient buffer, inside backward" if args.reduce == "backward"
-                   else "one call on the flattened leaf gradients after backward (DDP-style)"))
-            line["reduce_mode"] = args.reduce
+            if args.reduce == "backward" and args.sh_exchange == "factored":
+                line["limiting_collective"] = (
+                    f"inside backward: ncclAllGather of [P,3] colour gradients + camera centre ({12 * P / 1e6:.0f} MB sent, "
+                    f"{12 * P * world / 1e6:.0f} MB received per rank; the [P,M,3] SH gradient is rebuilt locally by "
+                    f"sh_grad_expand) + ncclAllReduce(SUM, fp32) of the other parameter gradients (11 floats/Gaussian = "
+                    f"{44 * P / 1e6:.0f} MB)")
+            else:
+                line["limiting_collective"] = (
+                    f"ncclAllReduce(SUM, fp32) of the parameter gradients: {floats} floats/Gaussian = {floats * 4 * P / 1e6:.0f} MB/step "
+                    + ("one call on the rasterizer's flat gradient buffer, inside backward" if args.reduce == "backward"
+                       else "one call on the flattened leaf gradients after backward (DDP-style)"))
+            line["reduce_mode"] = args.reduce if args.reduce != "backward" else f"backward/{args.sh_exchange}"
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_dict(wl, cpu_oracle_step(wl, 0))
         print(json.dumps(line), flush=True)

@@ -16,7 +16,7 @@ EXPORTS = ["b200gsr_version", "b200gsr_last_error", "b200gsr_saved_layout_query"
            "b200gsr_disparity_backward", "b200gsr_densify_stats", "b200gsr_densify_scratch_bytes",
            "b200gsr_densify_plan", "b200gsr_densify_map", "b200gsr_compact_plan", "b200gsr_gather_rows",
            "b200gsr_split_children", "b200gsr_kth_smallest", "b200gsr_views_geometry", "b200gsr_forward_views",
-           "b200gsr_backward_views"]
+           "b200gsr_backward_views", "b200gsr_sh_grad_expand"]
 
 
 class Params(C.Structure):
@@ -95,6 +95,8 @@ def load():
     lib.b200gsr_backward_ex.argtypes = lib.b200gsr_backward.argtypes[:-1] + [u32, i32, i32, i32, vp]
     lib.b200gsr_backward_ex.restype = C.c_int
     lib.b200gsr_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]
+    lib.b200gsr_sh_grad_expand.argtypes = [i32, i32, i32, i32, vp, vp, sz, vp, vp]
+    lib.b200gsr_sh_grad_expand.restype = C.c_int
     lib.b200gsr_dist2_scratch_bytes.argtypes = [i32]
     lib.b200gsr_dist2_scratch_bytes.restype = C.c_size_t
     lib.b200gsr_dist2_knn3.argtypes = [i32, vp, vp, vp, sz, vp]

@@ -253,8 +253,10 @@ int b200gsr_backward_ex(const b200gsr_params* prm, const float* means3D, const f
     if (prm->P == 0) return B200GSR_OK;
     if (g_begin < 0 || g_end > prm->P || g_begin > g_end || (g_begin % 128) != 0)
         return fail(B200GSR_ERR_BAD_ARG, "bad Gaussian range [%d, %d): need 0 <= begin <= end <= P, begin %% 128 == 0", g_begin, g_end);
-    if (shs && dsh_coefs != 0 && (dsh_coefs < (prm->sh_degree + 1) * (prm->sh_degree + 1) || dsh_coefs > prm->M))
-        return fail(B200GSR_ERR_BAD_ARG, "dsh_coefs=%d must be 0 or in [(sh_degree+1)^2, M]", dsh_coefs);
+    if (shs && dsh_coefs != 0 && dsh_coefs != -1 &&
+        (dsh_coefs < (prm->sh_degree + 1) * (prm->sh_degree + 1) || dsh_coefs > prm->M))
+        return fail(B200GSR_ERR_BAD_ARG, "dsh_coefs=%d must be 0, -1 or in [(sh_degree+1)^2, M]", dsh_coefs);
+    if (!shs && dsh_coefs < 0) return fail(B200GSR_ERR_BAD_ARG, "dsh_coefs=-1 (factored SH gradient) needs shs");
     if (!radii || !out_depth_alpha || !dL_dcolor || !dL_ddepth_alpha || !saved)
         return fail(B200GSR_ERR_BAD_ARG, "null saved-state/gradient pointer");
     if (!d_means3D || !d_means2D || !d_opacities || (shs && !d_shs) || (colors_precomp && !d_colors) ||
@@ -629,6 +631,15 @@ int b200gsr_dist2_knn3(int32_t P, const float* points, float* out, void* scratch
                     gsr_knn_scratch_bytes(P, nullptr));
     return check_cuda(gsr_launch_knn(P, points, out, static_cast<uint8_t*>(scratch), static_cast<cudaStream_t>(stream)),
                       "dist2_knn3");
+}
+
+int b200gsr_sh_grad_expand(int32_t P, int32_t M, int32_t sh_degree, int32_t num_views, const float* means3D,
+                           const float* dcol, size_t view_stride, float* d_shs, void* stream) {
+    if (P < 0 || M < 1 || num_views < 1 || num_views > 64 || sh_degree < 0 || sh_degree > 3 ||
+        M < (sh_degree + 1) * (sh_degree + 1) || view_stride < 3 * (size_t)P + 3 || (P > 0 && (!means3D || !dcol || !d_shs)))
+        return fail(B200GSR_ERR_BAD_ARG, "bad sh_grad_expand arguments");
+    return check_cuda(gsr_launch_sh_grad_expand(P, M, sh_degree, num_views, means3D, dcol, view_stride, d_shs,
+                                                static_cast<cudaStream_t>(stream)), "sh_grad_expand");
 }
 
 int b200gsr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,

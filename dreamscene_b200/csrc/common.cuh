@@ -216,6 +216,8 @@ cudaError_t gsr_launch_sort(const GsrFwdArgs& a, cudaStream_t side, cudaEvent_t 
 cudaError_t gsr_launch_composite_fwd(const GsrFwdArgs& a);
 cudaError_t gsr_launch_composite_bwd(const GsrBwdArgs& a);
 cudaError_t gsr_launch_project_bwd(const GsrBwdArgs& a);
+cudaError_t gsr_launch_sh_grad_expand(int P, int M, int deg, int nviews, const float* means3D, const float* dcol,
+                                      size_t stride, float* d_shs, cudaStream_t s);
 cudaError_t gsr_launch_mark_visible(int P, const float* means3D, const float* view,
                                     const float* proj, uint8_t* visible, cudaStream_t s);
 

@@ -468,6 +468,8 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
     float dmean[3] = {0.f, 0.f, 0.f};
     float dm2[2] = {0.f, 0.f};
     float dop = 0.f;
+    float dc3o[3] = {0.f, 0.f, 0.f};     // factored SH gradient (dsh_coefs < 0): dL/d(clamped colour), see below
+    const bool factored = dsh_coefs < 0;
     float dsc[3] = {0.f, 0.f, 0.f};
     float drot[4] = {0.f, 0.f, 0.f, 0.f};
     float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -595,7 +597,7 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
             sh_color(B, row, nf, raw);
             float dc3[3];
 #pragma unroll
-            for (int c_ = 0; c_ < 3; ++c_) dc3[c_] = (raw[c_] < 0.0f) ? 0.0f : drgb[c_];
+            for (int c_ = 0; c_ < 3; ++c_) { dc3[c_] = (raw[c_] < 0.0f) ? 0.0f : drgb[c_]; dc3o[c_] = dc3[c_]; }
             // s_k = sum_c dL/drgb_c * sh[k][c]; then overwrite the row with dL/dsh (float4 chunks)
             float s[16];
 #pragma unroll
@@ -616,7 +618,7 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
                             o[e] = B[f / 3] * dc3[f % 3];
                         }
                     }
-                    r4[q] = make_float4(o[0], o[1], o[2], o[3]);
+                    if (!factored) r4[q] = make_float4(o[0], o[1], o[2], o[3]);
                 }
             }
             if (deg > 0) {
@@ -675,7 +677,16 @@ project_bwd_kernel(b200gsr_params p, const float* __restrict__ means3D,
             GSR_OUT(d_colors + 3 * (size_t)i + 2, dcol[2], 4);
         }
     }
-    if (shs != nullptr) {
+    if (shs != nullptr && factored) {
+        // Factored SH gradient: dL/dsh[k][c] = basis_k(view direction) * dL/d(clamped colour)[c], so the three
+        // colour gradients are all another rank needs to rebuild this view's [M, 3] rows (it knows the mean and
+        // this view's camera centre): the multi-GPU payload drops from 3*M to 3 floats per Gaussian
+        // (b200gsr_sh_grad_expand).  d_shs is a [P, 3] array here.
+        if (active) {
+            GSR_OUT(d_shs + 3 * (size_t)i, dc3o[0], 4); GSR_OUT(d_shs + 3 * (size_t)i + 1, dc3o[1], 4);
+            GSR_OUT(d_shs + 3 * (size_t)i + 2, dc3o[2], 4);
+        }
+    } else if (shs != nullptr) {
         // drain the rows with coalesced stores (zeros for culled rows / inactive degrees)
         __syncthreads();
         const int nf = 3 * ncoef, nchunk = (nf + 3) >> 2;
@@ -781,7 +792,8 @@ static void launch_project_bwd_v(const GsrBwdArgs& a, int g_begin, int g_end, si
         a.prm, a.means3D, a.shs, a.colors, a.scales, a.rots, a.cov3d, a.radii,
         reinterpret_cast<float*>(a.saved + a.vl.dgeom),
         reinterpret_cast<uint32_t*>(a.saved + a.vl.header) + GSR_H_BWD_QUEUE, g_begin, g_end,
-        a.dsh_coefs > 0 ? a.dsh_coefs : a.prm.M, a.view * a.P_view, a.accumulate, a.d_means3D, a.d_means2D, a.d_shs,
+        a.dsh_coefs > 0 ? a.dsh_coefs : (a.dsh_coefs < 0 ? -1 : a.prm.M), a.view * a.P_view, a.accumulate, a.d_means3D,
+        a.d_means2D, a.d_shs,
         a.d_colors, a.d_opac, a.d_scales, a.d_rots, a.d_cov3d);
 }
 
@@ -806,6 +818,71 @@ cudaError_t gsr_launch_project_bwd(const GsrBwdArgs& a) {
     if (a.shs && a.prm.M == 16) launch_project_bwd<16>(a, g_begin, g_end, smem);
     else if (a.shs && a.prm.M == 4) launch_project_bwd<4>(a, g_begin, g_end, smem);
     else launch_project_bwd<0>(a, g_begin, g_end, smem);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Rebuild the summed SH gradient of `nviews` views from their factored form (project_bwd with
+// dsh_coefs < 0): d_shs[i][k][c] = sum_v basis_k(normalize(mean_i - cam_v)) * dcol_v[i][c].
+// View v's record starts at dcol + v * stride floats: [P][3] colour gradients, then its camera centre (3 floats).
+// The sum runs over v = 0 .. nviews-1 in order on every rank, so all ranks get bit-identical gradients.
+// ---------------------------------------------------------------------------------------------
+constexpr int kExpandViews = 64;
+__global__ void __launch_bounds__(kBlock)
+sh_grad_expand_kernel(int P, int M, int deg, int nviews, const float* __restrict__ means3D,
+                      const float* __restrict__ dcol, size_t stride, float* __restrict__ d_shs) {
+    extern __shared__ __align__(16) float ex_buf[];      // [kBlock][3*M] rows, drained with coalesced float4 stores
+    __shared__ float cam_s[3 * kExpandViews];
+    const int g0 = blockIdx.x * kBlock, i = g0 + threadIdx.x;
+    const int ncoef = (deg + 1) * (deg + 1), nrow = 3 * M;
+    for (int t = threadIdx.x; t < 3 * nviews; t += kBlock)
+        cam_s[t] = __ldg(dcol + (size_t)(t / 3) * stride + 3 * (size_t)P + (t % 3));
+    __syncthreads();
+    float acc[16][3];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { acc[k][0] = 0.f; acc[k][1] = 0.f; acc[k][2] = 0.f; }
+    if (i < P) {
+        const float x = __ldg(means3D + 3 * (size_t)i), y = __ldg(means3D + 3 * (size_t)i + 1), z = __ldg(means3D + 3 * (size_t)i + 2);
+        for (int v = 0; v < nviews; ++v) {
+            const float* dc = dcol + (size_t)v * stride + 3 * (size_t)i;
+            const float d0 = __ldg(dc), d1 = __ldg(dc + 1), d2 = __ldg(dc + 2);
+            if (d0 == 0.f && d1 == 0.f && d2 == 0.f) continue;       // culled / clamped in this view
+            const float vx = x - cam_s[3 * v], vy = y - cam_s[3 * v + 1], vz = z - cam_s[3 * v + 2];
+            float dn = sqrtf(vx * vx + vy * vy + vz * vz);
+            if (dn == 0.0f) dn = 1.0f;
+            float B[16];
+            sh_basis(deg, vx / dn, vy / dn, vz / dn, B);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                acc[k][0] = fmaf(B[k], d0, acc[k][0]); acc[k][1] = fmaf(B[k], d1, acc[k][1]); acc[k][2] = fmaf(B[k], d2, acc[k][2]);
+            }
+        }
+    }
+    float* row = ex_buf + (size_t)threadIdx.x * nrow;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        if (k < M) { row[3 * k] = k < ncoef ? acc[k][0] : 0.f; row[3 * k + 1] = k < ncoef ? acc[k][1] : 0.f; row[3 * k + 2] = k < ncoef ? acc[k][2] : 0.f; }
+    for (int k = 16; k < M; ++k) { row[3 * k] = 0.f; row[3 * k + 1] = 0.f; row[3 * k + 2] = 0.f; }
+    __syncthreads();
+    const int rows = min(kBlock, P - g0);
+    const size_t nf = (size_t)rows * nrow;
+    float* base = d_shs + (size_t)g0 * nrow;                 // 16-byte aligned when nrow*kBlock*4 % 16 == 0 (always: kBlock = 128)
+    const size_t n4 = nf >> 2;
+    for (size_t q = threadIdx.x; q < n4; q += kBlock)
+        reinterpret_cast<float4*>(base)[q] = reinterpret_cast<const float4*>(ex_buf)[q];
+    for (size_t f = (n4 << 2) + threadIdx.x; f < nf; f += kBlock) base[f] = ex_buf[f];
+}
+
+cudaError_t gsr_launch_sh_grad_expand(int P, int M, int deg, int nviews, const float* means3D, const float* dcol,
+                                      size_t stride, float* d_shs, cudaStream_t s) {
+    if (P == 0) return cudaSuccess;
+    if (nviews < 1 || nviews > kExpandViews || deg < 0 || deg > 3 || M < (deg + 1) * (deg + 1)) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)kBlock * 3 * M * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(sh_grad_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    sh_grad_expand_kernel<<<(P + kBlock - 1) / kBlock, kBlock, smem, s>>>(P, M, deg, nviews, means3D, dcol, stride, d_shs);
     return cudaGetLastError();
 }
 

@@ -19,12 +19,15 @@ are summed over NCCL/NVLink.  Two ways to do the sum, both additive to the refer
    finished chunks with the per-Gaussian backward of the rest; measured on 4 x B200 this LOSES
    (1.82 vs 1.44 ms/step at K=8: 40 small collectives cost more than the 0.14 ms of project_bwd they
    can hide; profiles/r02_scale_probe.md), so the default is K=1.
+   By default the SH gradient is not all-reduced at all: dL/dsh of a view is basis(view direction) x
+   dL/dcolour, so the ranks all-gather 3 floats per Gaussian (+ their camera centre) and rebuild the summed
+   [P, M, 3] rows locally (``exchange_factored``; sh_exchange="dense" restores the row all-reduce).
    This mode reduces the gradient AT THE RASTERIZER INPUTS, so it equals the sequential sum
    only when the map parameters -> rasterizer inputs is the same deterministic function on every
    rank (inputs are leaves, or activations without per-rank randomness).  Every rank must issue the
    same sequence of rasterizer backward calls with the same P; set B200GSR_CHECK_COLLECTIVES=1 to
-   verify that at run time.  ``no_sync()`` suspends the reduction while a rank accumulates several
-   local views and reduces once with the last one.
+   verify that at run time.  ``no_sync()`` suspends the in-backward reduction (a rank that renders several
+   local views per step accumulates them in the leaves and calls ``all_reduce_gradients`` once).
 
 Per-view quantities (means2D grad, radii, visibility) are NOT reduced, as in the reference, which only
 uses the last view's (training/object_trainer.py:385-390).
@@ -41,21 +44,27 @@ import torch.distributed as dist
 _group = None
 _enabled = False
 _chunks = 1
+_sh_exchange = "factored"
 _suspended = 0
+MAX_FACTORED_VIEWS = 64          # b200gsr_sh_grad_expand
 _CHECK = bool(int(os.environ.get("B200GSR_CHECK_COLLECTIVES", "0")))
 
 
-def enable_view_sharding(group: Optional["dist.ProcessGroup"] = None, mode: str = "backward", chunks: int = 1) -> None:
+def enable_view_sharding(group: Optional["dist.ProcessGroup"] = None, mode: str = "backward", chunks: int = 1,
+                         sh_exchange: str = "factored") -> None:
     """mode="backward": every rasterizer backward all-reduces its parameter gradients (see the module
     docstring for when that is exact); mode="deferred": nothing happens inside backward, call
     all_reduce_gradients() yourself.  `chunks` = number of Gaussian ranges the in-backward
-    reduction is pipelined over."""
-    global _group, _enabled, _chunks
+    reduction is pipelined over.  sh_exchange="factored" (default, chunks == 1, SH inputs): the SH gradient
+    is exchanged as 3 floats per Gaussian and view and rebuilt on every rank; "dense": all-reduced as rows."""
+    global _group, _enabled, _chunks, _sh_exchange
     if not dist.is_initialized():
         raise RuntimeError("torch.distributed is not initialised")
     if mode not in ("backward", "deferred"):
         raise ValueError("mode must be 'backward' or 'deferred'")
-    _group, _enabled, _chunks = group, mode == "backward", max(1, int(chunks))
+    if sh_exchange not in ("factored", "dense"):
+        raise ValueError("sh_exchange must be 'factored' or 'dense'")
+    _group, _enabled, _chunks, _sh_exchange = group, mode == "backward", max(1, int(chunks)), sh_exchange
 
 
 def disable_view_sharding() -> None:
@@ -80,6 +89,48 @@ def no_sync():
 
 def reduction_active() -> bool:
     return _enabled and _suspended == 0 and dist.is_initialized() and dist.get_world_size(_group) > 1
+
+
+def factored_sh_exchange() -> bool:
+    """The in-backward reduction sends the SH gradient in factored form (see exchange_factored)."""
+    return (reduction_active() and _sh_exchange == "factored" and _chunks <= 1
+            and dist.get_world_size(_group) <= MAX_FACTORED_VIEWS)
+
+
+def factored_stride(P: int) -> int:
+    """Floats per rank in the all-gathered buffer: [P, 3] colour gradients + camera centre, padded to 256 B."""
+    return (3 * P + 3 + 63) // 64 * 64
+
+
+def exchange_factored(flat: torch.Tensor, dcol: torch.Tensor, P: int, M: int, sh_degree: int,
+                      means3D: torch.Tensor) -> torch.Tensor:
+    """Reduction of one backward under view sharding with the SH gradient in factored form.
+
+    dL/dsh of a view is the outer product basis(view direction of the Gaussian) x dL/d(clamped colour): instead
+    of all-reducing [P, M, 3] rows (192 of the 236 bytes per Gaussian at M = 16) every rank contributes `dcol` =
+    [P, 3] colour gradients + its camera centre, ONE all-gather hands everybody all of them, and
+    b200gsr_sh_grad_expand rebuilds the summed rows locally (views in rank order: bit-identical on every rank).
+    `flat` (means3D / opacity / scale / rotation gradients, 44 bytes per Gaussian) is all-reduced as before.
+    Exact under the same condition as the dense in-backward reduction plus: all ranks pass the same means3D."""
+    from . import _lib
+    world = dist.get_world_size(_group)
+    if _CHECK:
+        _check_same_size(flat.numel() + dcol.numel(), flat.device)
+    gathered = torch.empty(world, dcol.numel(), dtype=torch.float32, device=dcol.device)
+    works = [dist.all_gather_into_tensor(gathered, dcol, group=_group, async_op=True)]
+    if flat.numel() > 0:
+        works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=_group, async_op=True))
+    for w in works:
+        w.wait()
+    d_sh = torch.empty(P, M, 3, dtype=torch.float32, device=dcol.device)
+    import ctypes as C
+    with torch.cuda.device(dcol.device):
+        rc = _lib.load().b200gsr_sh_grad_expand(
+            P, M, int(sh_degree), world, C.c_void_p(means3D.data_ptr()), C.c_void_p(gathered.data_ptr()),
+            dcol.numel(), C.c_void_p(d_sh.data_ptr()), C.c_void_p(torch.cuda.current_stream(dcol.device).cuda_stream))
+    if rc:
+        raise RuntimeError(f"b200gsr_sh_grad_expand failed ({rc}): {_lib.last_error()}")
+    return d_sh
 
 
 def chunk_bounds(P: int, chunks: Optional[int] = None, align: int = 128):

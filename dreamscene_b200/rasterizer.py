@@ -407,8 +407,10 @@ class _RasterizeGaussians(torch.autograd.Function):
         # 14 instead of 59 floats per Gaussian); otherwise it is simply one allocation.
         reduce = P > 0 and _parallel.reduction_active()
         ncoef = (int(rs.sh_degree) + 1) ** 2
-        compact = reduce and has_sh and ncoef < M
-        n_col = (3 * ncoef if compact else 3 * M) if has_sh else 3
+        # factored: the SH gradient leaves the kernel as dL/dcolour [P, 3] and is exchanged by all-gather
+        factored = reduce and has_sh and _parallel.factored_sh_exchange()
+        compact = reduce and has_sh and ncoef < M and not factored
+        n_col = 0 if factored else ((3 * ncoef if compact else 3 * M) if has_sh else 3)
         offs, o = grad_sections(P, n_col, has_sr)
         flat = torch.empty(max(o, 1), dtype=torch.float32, device=dev)
         widths = {"means3D": 3, "opac": 1, "col": n_col, "scales": 3, "rots": 4, "cov": 6}
@@ -416,7 +418,10 @@ class _RasterizeGaussians(torch.autograd.Function):
         d_means3D = sec("means3D").view(P, 3)
         d_opac = sec("opac").view(P, 1)
         d_colsh = sec("col")
-        d_sh = d_colsh.view(P, n_col // 3, 3) if has_sh else None
+        if factored:
+            d_sh = torch.empty(_parallel.factored_stride(P), dtype=torch.float32, device=dev)   # [P,3] + camera centre
+        else:
+            d_sh = d_colsh.view(P, n_col // 3, 3) if has_sh else None
         d_colors = d_colsh.view(P, 3) if has_col else None
         if has_sr:
             d_scales = sec("scales").view(P, 3)
@@ -443,13 +448,18 @@ class _RasterizeGaussians(torch.autograd.Function):
                         _ptr(rots), _ptr(cov3d), _ptr(radii), _ptr(depth_alpha), _ptr(g_color), _ptr(g_da),
                         _ptr(st.saved), st.saved.numel(), None, 0, st.capacity,
                         _ptr(d_means3D), _ptr(d_means2D), _ptr(d_sh), _ptr(d_colors), _ptr(d_opac),
-                        _ptr(d_scales), _ptr(d_rots), _ptr(d_cov), stages, g0, g1, ncoef if compact else 0, stream)
+                        _ptr(d_scales), _ptr(d_rots), _ptr(d_cov), stages, g0, g1,
+                        -1 if factored else (ncoef if compact else 0), stream)
                     if rc:
                         raise RuntimeError(f"b200gsr_backward failed ({rc}): {_lib.last_error()}")
 
                 bounds = _parallel.chunk_bounds(P) if reduce else []
                 if not reduce:
                     launch(_lib.BWD_COMPOSITE | _lib.BWD_PROJECT, 0, P)
+                elif factored:
+                    launch(_lib.BWD_COMPOSITE | _lib.BWD_PROJECT, 0, P)
+                    d_sh[3 * P:3 * P + 3].copy_(_const(rs.campos, dev).reshape(3))
+                    d_sh = _parallel.exchange_factored(flat[:o], d_sh, P, M, int(rs.sh_degree), means3D)
                 elif len(bounds) <= 1:
                     launch(_lib.BWD_COMPOSITE | _lib.BWD_PROJECT, 0, P)
                     _parallel.maybe_all_reduce(flat[:o] if o > 0 else flat)      # ONE ncclAllReduce of the flat buffer

@@ -168,7 +168,10 @@ int b200gsr_backward(const b200gsr_params* prm,
  *               every Gaussian must be covered exactly once per backward (read-and-clear);
  *   dsh_coefs : 0 = d_shs has the reference layout [P, M, 3]; otherwise d_shs is a COMPACT
  *               [P, dsh_coefs, 3] array holding only the coefficients an active degree can touch
- *               ((sh_degree+1)^2 <= dsh_coefs <= M): the multi-GPU gradient payload at low degrees.
+ *               ((sh_degree+1)^2 <= dsh_coefs <= M): the multi-GPU gradient payload at low degrees;
+ *               -1 = FACTORED: d_shs is a [P, 3] array receiving dL/d(clamped colour).  The SH gradient of a
+ *               view is the outer product basis(view direction) x that vector, so ranks exchange 3 floats per
+ *               Gaussian and view instead of 3*M and rebuild the sum with b200gsr_sh_grad_expand.
  */
 #define B200GSR_BWD_COMPOSITE 1u
 #define B200GSR_BWD_PROJECT 2u
@@ -184,6 +187,16 @@ int b200gsr_backward_ex(const b200gsr_params* prm,
                         float* d_opacities, float* d_scales, float* d_rotations, float* d_cov3D,
                         uint32_t stages, int32_t g_begin, int32_t g_end, int32_t dsh_coefs,
                         void* stream);
+
+/*
+ * Sum of the SH gradients of `num_views` views from their factored form (additive; multi-GPU view sharding):
+ *   d_shs[i][k][c] = sum_v basis_k(normalize(means3D[i] - cam_v)) * dcol_v[i][c],  coefficients above sh_degree = 0.
+ * View v's record starts at dcol + v * view_stride floats: [P][3] from b200gsr_backward_ex(dsh_coefs = -1), followed
+ * by the view's camera centre (3 floats) - exactly what one all-gather of per-rank [3P + 3 (+pad)] buffers delivers.
+ * The sum runs in view order, so every rank computes bit-identical gradients.  1 <= num_views <= 64.
+ */
+int b200gsr_sh_grad_expand(int32_t P, int32_t M, int32_t sh_degree, int32_t num_views, const float* means3D,
+                           const float* dcol, size_t view_stride, float* d_shs, void* stream);
 
 /*
  * Multi-view rendering (additive, no upstream equivalent): B views of the same image

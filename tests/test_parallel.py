@@ -104,7 +104,11 @@ def _nccl_worker(rank, world, port, q):
         t = {k: v.to(dev).requires_grad_(True) for k, v in sc.items()}
         m2d = torch.zeros(P, 3, device=dev, requires_grad=True)
         if mode == "backward":
-            parallel.enable_view_sharding(chunks=3)
+            parallel.enable_view_sharding(chunks=3)                  # chunk-pipelined dense all-reduce
+        elif mode == "factored":
+            parallel.enable_view_sharding()                          # default: factored SH exchange (all-gather + expand)
+        elif mode == "dense":
+            parallel.enable_view_sharding(sh_exchange="dense")       # one all-reduce of the flat buffer incl. SH rows
         elif mode == "deferred":
             parallel.enable_view_sharding(mode="deferred")
         else:
@@ -124,13 +128,18 @@ def _nccl_worker(rank, world, port, q):
 
     ok = True
     for deg in (3, 1, 0):       # degree < 3: only the active SH columns travel (compact payload)
-        reduced, m2d_own = view_grads(rank, deg, "backward")
         seq = sum(view_grads(v, deg, "off")[0] for v in range(world))       # sequential loop on one GPU
-        err = float((reduced - seq).norm() / seq.norm())
         _, m2d_seq = view_grads(rank, deg, "off")
-        # per-view means2D grads are NOT reduced (equal up to the fp32 atomic summation order)
-        ok = ok and err < 1e-5 and float((m2d_own - m2d_seq).norm() / m2d_seq.norm()) < 1e-5
-        results[f"backward_deg{deg}"] = err
+        for mode in ("backward", "factored", "dense"):
+            reduced, m2d_own = view_grads(rank, deg, mode)
+            err = float((reduced - seq).norm() / seq.norm())
+            # per-view means2D grads are NOT reduced (equal up to the fp32 atomic summation order)
+            ok = ok and err < 1e-5 and float((m2d_own - m2d_seq).norm() / m2d_seq.norm()) < 1e-5
+            results[f"{mode}_deg{deg}"] = err
+            if mode == "factored":      # views are summed in rank order on every rank: bit-identical results
+                both = [torch.empty_like(reduced) for _ in range(world)]
+                dist.all_gather(both, reduced)
+                ok = ok and all(torch.equal(both[0], b) for b in both)
     # per-rank random augmentation between leaves and rasterizer: only the DDP-style reduction of the
     # LEAF gradients reproduces the sequential sum
     red, _ = view_grads(rank, 1, "deferred", noise_seed=100 + rank)
