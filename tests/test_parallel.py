@@ -48,6 +48,20 @@ def _gloo_worker(rank, world, port, q):
     untouched = grads[rank].clone()
     parallel.maybe_all_reduce(untouched)
     ok = ok and torch.equal(untouched, grads[rank]) and uneven_refused
+    # the factored SH exchange is the default of the in-backward reduction (one chunk, <= 64 ranks)
+    parallel.enable_view_sharding()
+    ok = ok and parallel.factored_sh_exchange()
+    parallel.enable_view_sharding(sh_exchange="dense")
+    ok = ok and parallel.reduction_active() and not parallel.factored_sh_exchange()
+    parallel.enable_view_sharding(chunks=3)
+    ok = ok and not parallel.factored_sh_exchange()
+    try:
+        parallel.enable_view_sharding(sh_exchange="sparse")
+        ok = False
+    except ValueError:
+        pass
+    ok = ok and parallel.factored_stride(1000) == 3008 and parallel.factored_stride(21) % 64 == 0 \
+        and parallel.factored_stride(21) >= 3 * 21 + 3
     # no_sync() suspends the in-backward reduction
     parallel.enable_view_sharding()
     with parallel.no_sync():
@@ -176,3 +190,32 @@ def test_chunk_bounds_cover_the_range_with_aligned_starts():
             assert all(g0 % 128 == 0 and g0 < g1 for g0, g1 in b)
             assert all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
     assert parallel.chunk_bounds(0) == []
+
+
+def test_sh_gradient_of_one_view_is_rank_one_per_gaussian_cpu_oracle():
+    """The identity the factored SH exchange rests on (parallel.exchange_factored), checked on the CPU oracle's autograd:
+    dL/dsh[i][k][c] = basis_k(direction of Gaussian i in this view) * dL/d(clamped colour)[i][c], and 0 above the active
+    degree - so 3 floats per Gaussian and view (plus the camera centre) determine the whole [M, 3] row."""
+    from oracle import splat_ref as O
+    from tests import util_scene as U
+    torch.set_num_threads(2)
+    for deg in (3, 1):
+        sc, _, _ = U.make_inputs(400, 48, 48, seed=31)
+        cam = U.cameras.orbit_camera(phi_deg=70.0, height=48, width=48)
+        S = U.oracle_settings(cam, deg)
+        t = {k: v.clone().requires_grad_(True) for k, v in sc.items()}
+        r = O.rasterize(S, t["means3D"], t["opacities"], shs=t["shs"], scales=t["scales"], rotations=t["rotations"])
+        g = torch.Generator().manual_seed(5)
+        (r["color"] * torch.randn(r["color"].shape, generator=g)).sum().backward()
+        d_sh = t["shs"].grad                                                    # [P, M, 3]
+        P, M, ncoef = d_sh.shape[0], d_sh.shape[1], (deg + 1) ** 2
+        d = sc["means3D"] - cam.camera_center.reshape(1, 3)
+        d = d / d.norm(dim=1, keepdim=True)
+        basis = torch.stack([O.eval_sh_basis_dot(deg, torch.nn.functional.one_hot(torch.full((P,), k), M)[:, :, None]
+                                                 .expand(P, M, 3).float(), d)[:, 0] for k in range(ncoef)], dim=1)   # [P, ncoef]
+        dcol = d_sh[:, 0, :] / basis[:, :1]                                     # basis_0 is the constant SH_C0
+        rebuilt = basis[:, :, None] * dcol[:, None, :]
+        touched = d_sh.abs().sum(dim=(1, 2)) > 0
+        assert int(touched.sum()) > 50
+        assert float((rebuilt - d_sh[:, :ncoef]).abs().max()) <= 1e-6 * float(d_sh.abs().max())
+        assert float(d_sh[:, ncoef:].abs().max()) == 0.0 if ncoef < M else True
