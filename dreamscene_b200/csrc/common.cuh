@@ -63,7 +63,7 @@ __host__ __device__ inline int gsr_bwd_class(uint32_t n) {     // n >= 1
 #ifdef __CUDA_ARCH__
     const int e = 31 - __clz((int)n);
 #else
-    int e = 0; while ((n >> (e + 1)) != 0u) ++e;
+    int e = 0; while (e < 31 && (n >> (e + 1)) != 0u) ++e;
 #endif
     const int k = 2 * e + (e > 0 ? (int)((n >> (e - 1)) & 1u) : 0);
     return k < GSR_BWD_CLASSES - 1 ? k : GSR_BWD_CLASSES - 1;

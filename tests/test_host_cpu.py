@@ -128,3 +128,19 @@ def test_deferred_overflow_check_reads_the_notify_ring_without_blocking():
     with pytest.raises(R.PairCapacityOverflow):
         R._resolve_pending(d)
     assert not d.pending and d.capacity >= 6 << 20      # raised so that a retry fits
+
+
+def test_shared_inline_helpers_native_check(tmp_path):
+    """common.cuh helpers used by both host and device code (multisplit grid, backward size classes, tile grid):
+    tests/native/common_check.cu is compiled with nvcc and run on the CPU."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "common_check")
+    src = os.path.join(ROOT, "tests", "native", "common_check.cu")
+    subprocess.run([nvcc, "-std=c++17", "-Wno-deprecated-gpu-targets", "-I", os.path.join(ROOT, "dreamscene_b200", "csrc"),
+                    "-I", os.path.join(ROOT, "include"), "-o", exe, src], check=True, timeout=300)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "helpers ok" in out.stdout, out.stdout + out.stderr
